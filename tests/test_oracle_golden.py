@@ -1,0 +1,174 @@
+"""Pin the CPU oracle (oracle/) against golden vectors produced by executing the
+reference's own Python functions (tests/make_golden.py) and against the known
+answers recorded in SURVEY.md §8c.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import oracle as orc
+from oracle import simple_flows as sf
+
+
+def load(golden_dir, name):
+    return np.load(os.path.join(golden_dir, name))
+
+
+def rel_err(a, b):
+    return np.max(np.abs(a - b) / np.maximum(np.abs(b), 1e-300))
+
+
+def test_stream_is_np_roll_bitexact(golden_dir):
+    g = load(golden_dir, "streaming_roll.npz")         # PyLB/Streaming.py:33-46
+    for tag in "abc":
+        f = g["in_" + tag].copy()
+        orc.stream(f)
+        assert np.array_equal(f, g["out_" + tag])
+
+
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+def test_cavity_stream_and_bounce_back_bitexact(golden_dir, dt):
+    g = load(golden_dir, "cavity_opt2_bb_%s.npz" % dt)  # cavity_opt2.py:109-177
+    for tag in "abcde":
+        f = g["in_" + tag].copy()
+        u0 = float(g["u0_" + tag])
+        orc.cavity_stream_and_bounce_back(f, u0)
+        assert np.array_equal(f, g["out_" + tag]), tag
+        orc.cavity_stream_and_bounce_back(f, u0)
+        orc.cavity_stream_and_bounce_back(f, u0)
+        assert np.array_equal(f, g["out3_" + tag]), tag
+
+
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+@pytest.mark.parametrize("walls_lr", [True, False])
+def test_pull_formulation_equals_literal_sequence(dt, walls_lr):
+    """the fused pull rule == roll-then-overwrite, bitwise."""
+    for nx, ny in [(24, 20), (7, 5), (16, 33), (3, 3), (2, 2), (40, 2)]:
+        f = orc.perturbed_state(nx, ny, np.dtype(dt), seed=nx * ny)
+        a = f.copy()
+        b = np.empty_like(f)
+        for step in range(5):
+            orc.cavity_stream_and_bounce_back(a, 0.1, walls_lr)
+            orc.cavity_step_pull(f, b, 1.7, 0.1, walls_lr, do_collide=False)
+            assert np.array_equal(a, b), (nx, ny, step)
+            orc.collide(a, 1.7)
+            orc.collide(b, 1.7)
+            f, b = b, f
+
+
+def test_pull_run_equals_literal_run_200_steps():
+    f = orc.init_equilibrium(24, 20)
+    a = f.copy()
+    orc.cavity_run(a, 1.7, 200)
+    b = np.empty_like(f)
+    for _ in range(200):
+        orc.cavity_step_pull(f, b, 1.7)
+        f, b = b, f
+    assert np.array_equal(a, f)
+
+
+def test_periodic_pull_equals_roll():
+    f = orc.perturbed_state(9, 13, seed=3)
+    a = f.copy()
+    b = np.empty_like(f)
+    orc.stream(a)
+    orc.periodic_step_pull(f, b, 1.0, do_collide=False)
+    assert np.array_equal(a, b)
+
+
+def test_equilibrium_and_collide_vs_reference_test_formulas(golden_dir):
+    """tests/02-CollideTest.py:94-111 with the reference's tolerance (1e-7, PyLBTest.py:75)."""
+    g = load(golden_dir, "collide_test_ref.npz")
+    for p in ("eq", "eq2"):
+        rho, ux, uy = g[p + "_rho"], g[p + "_ux"], g[p + "_uy"]
+        e = np.zeros((9,) + rho.shape)
+        orc.equilibrium(rho.reshape(-1).copy(), ux.reshape(-1).copy(), uy.reshape(-1).copy(), e.reshape(9, -1))
+        assert np.abs(e - g[p + "_out"]).max() < 1e-7
+        assert np.abs(e - g[p + "_out"]).max() < 1e-14      # what is actually achieved
+    for omega in (0.5, 1.7):
+        c = g["col_in"].copy()
+        orc.collide(c.reshape(9, -1), omega)
+        assert np.abs(c - g["col_out_%s" % omega]).max() < 1e-7
+        assert np.abs(c - g["col_out_%s" % omega]).max() < 1e-13
+
+
+def test_collide_vs_opt0_matrix_form(golden_dir):
+    g = load(golden_dir, "cavity_opt0_collide.npz")    # cavity_opt0.py:93-138
+    c = g["f_in"].copy()
+    orc.collide(c, float(g["omega"]))
+    assert rel_err(c, g["f_out"]) < 1e-12
+
+
+def test_cavity_run_vs_opt1_numpy(golden_dir):
+    """cavity_opt1.py (numpy collide, different algebraic form) for 50 steps: 1e-12 relative."""
+    g = load(golden_dir, "cavity_opt1_run.npz")
+    f = g["f0"].copy()
+    done = 0
+    for n in (1, 10, 50):
+        orc.cavity_run(f, float(g["omega"]), n - done, float(g["u0"]))
+        done = n
+        assert rel_err(f, g["f_%d" % n]) < 1e-12, n
+    # the lid leaks mass at the corners, 480 -> 480.0409 after 50 steps
+    assert abs(f.sum() - 480.0409) < 1e-4
+    assert abs(f.sum() - float(g["mass_50"])) < 1e-9
+
+
+def test_shear_wave_vs_opt1_numpy(golden_dir):
+    g = load(golden_dir, "shear_opt1_run.npz")         # shear_wave_opt1.py
+    f = g["f0"].copy()
+    ampl = orc.periodic_run(f, float(g["omega"]), int(g["nsteps"]), g["uy_k"])
+    assert rel_err(f, g["f_end"]) < 1e-12
+    assert np.max(np.abs(ampl - g["ampl"])) < 1e-14
+
+
+def test_shear_wave_known_answers_300x200():
+    """SURVEY.md §8c known answers: 300x200, omega=1, 1000 steps."""
+    nx, ny, a0 = 300, 200, 0.01
+    f, uy_k = orc.shear_wave_init(nx, ny, a0=a0)
+    ampl = orc.periodic_run(f, 1.0, 1000, uy_k)
+    a_init = (uy_k * uy_k).sum() * 2 / nx
+    assert abs(ampl[0] / a_init - 0.999926894492) < 1e-9
+    assert abs(ampl[-1] / a_init - 0.929500270576) < 1e-9
+    # viscosity from the decay a(t) = a0 exp(-nu k^2 t), analytic nu = (1/omega - 1/2)/3 = 1/6
+    kk = (2 * np.pi / nx) ** 2
+    t = np.arange(1, 1001)
+    nu = -np.polyfit(t, np.log(ampl / a_init), 1)[0] / kk
+    assert abs(nu - 1 / 6) / (1 / 6) < 1e-6
+
+
+def test_scalar_equilibrium_matches_array():
+    e = orc.equilibrium1(1.1, 0.05, -0.02)
+    f = np.zeros((9, 1))
+    orc.equilibrium(np.array([1.1]), np.array([0.05]), np.array([-0.02]), f)
+    assert np.array_equal(e, f[:, 0])
+    assert abs(e.sum() - 1.1) < 1e-15
+
+
+def test_simple_flows_couette_bitexact(golden_dir):
+    g = load(golden_dir, "simple_couette.npz")          # PoiseuilleFlow.py:93-111
+    f = g["f0"].copy()
+    assert np.array_equal(f, sf.feq(np.ones(f.shape[1:]), np.zeros(f.shape[1:]), np.zeros(f.shape[1:])))
+    for s in range(int(g["nsteps"])):
+        ux = sf.couette_step(f, float(g["omega"]), float(g["uw"]))
+        if "f_%d" % (s + 1) in g:
+            assert np.array_equal(f, g["f_%d" % (s + 1)]), s
+    assert np.array_equal(ux, g["ux_last"])
+
+
+def test_simple_flows_poiseuille_bitexact(golden_dir):
+    g = load(golden_dir, "simple_poiseuille.npz")       # PoiseuilleFlow.py:129-148
+    f = g["f0"].copy()
+    for s in range(int(g["nsteps"])):
+        ux = sf.poiseuille_step(f, float(g["omega"]), float(g["rho_in"]), float(g["rho_out"]))
+        if "f_%d" % (s + 1) in g:
+            assert np.array_equal(f, g["f_%d" % (s + 1)]), s
+    assert np.array_equal(ux, g["ux_last"])
+
+
+def test_simple_flows_sliding_lid_bitexact(golden_dir):
+    g = load(golden_dir, "simple_sliding_lid.npz")      # slidingLid.py:68-108
+    f = g["f0"].copy()
+    for s in range(int(g["nsteps"])):
+        sf.sliding_lid_step(f, float(g["omega"]), float(g["uw"]))
+        if "f_%d" % (s + 1) in g:
+            assert np.array_equal(f, g["f_%d" % (s + 1)]), s
