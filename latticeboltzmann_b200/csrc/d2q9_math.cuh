@@ -1,0 +1,125 @@
+// D2Q9 BGK arithmetic for the B200 kernels.
+//
+// Two flavours, selected by the EXACT template flag:
+//   EXACT = true : every operation is an individually rounded IEEE operation
+//                  (__dadd_rn / __dmul_rn / __ddiv_rn ... are never contracted
+//                  into FMAs by nvcc), in the expression order of the reference
+//                  (c/d2q9.h:59-81 equilibrium, c/d2q9.h:121-131 collide).  The
+//                  result is bit-identical to the reference's baseline x86-64
+//                  build (no -march => mulsd/addsd, no FMA).
+//   EXACT = false: same formulas written as plain C++ so that nvcc contracts
+//                  a*b+c into FMAs, with one reciprocal of rho and constant
+//                  divisions turned into multiplications.
+//
+// Three reference divisions are folded away exactly in EXACT mode:
+//   4*rho/9  == 4*(rho/9)   and   rho/36 == (rho/9)/4   (power-of-two scaling
+//   commutes with rounding),  x/2 == x*0.5.
+// That leaves 4 IEEE divisions per cell (rho/9, uu/6, ux/rho, uy/rho).
+#pragma once
+
+namespace lbm {
+
+// Channel order and velocities: PyLB/Streaming.py:28-29.
+//   i :  0   1   2   3   4   5   6   7   8
+//        .   E   N   W   S   NE  NW  SW  SE      (cavity_opt2.py:70)
+enum { Q0 = 0, QE = 1, QN = 2, QW = 3, QS = 4, QNE = 5, QNW = 6, QSW = 7, QSE = 8 };
+__host__ __device__ constexpr int cx_of(int i) { return i == 1 || i == 5 || i == 8 ? 1 : (i == 3 || i == 6 || i == 7 ? -1 : 0); }
+__host__ __device__ constexpr int cy_of(int i) { return i == 2 || i == 5 || i == 6 ? 1 : (i == 4 || i == 7 || i == 8 ? -1 : 0); }
+__host__ __device__ constexpr int opp_of(int i) { return i == 0 ? 0 : (i <= 4 ? ((i - 1 + 2) % 4) + 1 : ((i - 5 + 2) % 4) + 5); }
+
+// Individually rounded operations (never contracted).
+__device__ __forceinline__ double rn_add(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double rn_sub(double a, double b) { return __dsub_rn(a, b); }
+__device__ __forceinline__ double rn_mul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double rn_div(double a, double b) { return __ddiv_rn(a, b); }
+__device__ __forceinline__ float rn_add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float rn_sub(float a, float b) { return __fsub_rn(a, b); }
+__device__ __forceinline__ float rn_mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float rn_div(float a, float b) { return __fdiv_rn(a, b); }
+
+// c/d2q9.h:59-81
+template <typename T, bool EXACT>
+__device__ __forceinline__ void d2q9_equilibrium(T rho, T ux, T uy, T (&e)[9])
+{
+    if (EXACT) {
+        const T w1 = rn_div(rho, T(9));            // rho/9
+        const T w0 = rn_mul(T(4), w1);             // == (4*rho)/9 exactly
+        const T w5 = rn_mul(T(0.25), w1);          // == rho/36 exactly
+        ux = rn_mul(ux, T(3));
+        uy = rn_mul(uy, T(3));
+        const T cu5 = rn_add(ux, uy);
+        const T cu6 = rn_add(-ux, uy);
+        const T cu7 = rn_sub(-ux, uy);
+        const T cu8 = rn_sub(ux, uy);
+        const T uu = rn_div(rn_add(rn_mul(ux, ux), rn_mul(uy, uy)), T(6));
+        const T hx = rn_mul(rn_mul(ux, ux), T(0.5));
+        const T hy = rn_mul(rn_mul(uy, uy), T(0.5));
+        e[0] = rn_mul(w0, rn_sub(T(1), uu));
+        e[1] = rn_mul(w1, rn_sub(rn_add(rn_add(T(1), ux), hx), uu));
+        e[2] = rn_mul(w1, rn_sub(rn_add(rn_add(T(1), uy), hy), uu));
+        e[3] = rn_mul(w1, rn_sub(rn_add(rn_sub(T(1), ux), hx), uu));
+        e[4] = rn_mul(w1, rn_sub(rn_add(rn_sub(T(1), uy), hy), uu));
+        e[5] = rn_mul(w5, rn_sub(rn_add(rn_add(T(1), cu5), rn_mul(rn_mul(cu5, cu5), T(0.5))), uu));
+        e[6] = rn_mul(w5, rn_sub(rn_add(rn_add(T(1), cu6), rn_mul(rn_mul(cu6, cu6), T(0.5))), uu));
+        e[7] = rn_mul(w5, rn_sub(rn_add(rn_add(T(1), cu7), rn_mul(rn_mul(cu7, cu7), T(0.5))), uu));
+        e[8] = rn_mul(w5, rn_sub(rn_add(rn_add(T(1), cu8), rn_mul(rn_mul(cu8, cu8), T(0.5))), uu));
+    } else {
+        const T w1 = rho * T(1.0 / 9.0);
+        const T w0 = T(4) * w1;
+        const T w5 = T(0.25) * w1;
+        ux *= T(3);
+        uy *= T(3);
+        const T cu5 = ux + uy, cu6 = uy - ux;
+        const T base = T(1) - (ux * ux + uy * uy) * T(1.0 / 6.0);
+        const T bx = base + T(0.5) * ux * ux, by = base + T(0.5) * uy * uy;
+        const T b5 = base + T(0.5) * cu5 * cu5, b6 = base + T(0.5) * cu6 * cu6;
+        e[0] = w0 * base;
+        e[1] = w1 * (bx + ux);
+        e[2] = w1 * (by + uy);
+        e[3] = w1 * (bx - ux);
+        e[4] = w1 * (by - uy);
+        e[5] = w5 * (b5 + cu5);
+        e[6] = w5 * (b6 + cu6);
+        e[7] = w5 * (b5 - cu5);
+        e[8] = w5 * (b6 - cu6);
+    }
+}
+
+// c/d2q9.h:125-129 for one cell.  rho follows Eigen 3.4.0's unrolled redux tree
+// for a fixed-size 9-vector: ((f0+f1)+(f2+f3)) + ((f4+f5)+(f6+(f7+f8))).
+template <typename T, bool EXACT>
+__device__ __forceinline__ void d2q9_collide(T (&f)[9], T omega)
+{
+    T e[9];
+    if (EXACT) {
+        const T rho = rn_add(rn_add(rn_add(f[0], f[1]), rn_add(f[2], f[3])),
+                             rn_add(rn_add(f[4], f[5]), rn_add(f[6], rn_add(f[7], f[8]))));
+        const T sx = rn_add(rn_sub(rn_sub(rn_add(rn_sub(f[1], f[3]), f[5]), f[6]), f[7]), f[8]);
+        const T sy = rn_sub(rn_sub(rn_add(rn_add(rn_sub(f[2], f[4]), f[5]), f[6]), f[7]), f[8]);
+        d2q9_equilibrium<T, true>(rho, rn_div(sx, rho), rn_div(sy, rho), e);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = rn_add(f[i], rn_mul(omega, rn_sub(e[i], f[i])));
+    } else {
+        const T rho = ((f[0] + f[1]) + (f[2] + f[3])) + ((f[4] + f[5]) + (f[6] + (f[7] + f[8])));
+        const T sx = (f[1] - f[3]) + (f[5] - f[6]) + (f[8] - f[7]);
+        const T sy = (f[2] - f[4]) + (f[5] - f[8]) + (f[6] - f[7]);
+        const T inv = T(1) / rho;
+        d2q9_equilibrium<T, false>(rho, sx * inv, sy * inv, e);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = f[i] + omega * (e[i] - f[i]);
+    }
+}
+
+// Moments as the reference's drivers compute them for output
+// (cavity_opt2.py:280-281): rho = np.sum(f, axis=0) accumulates f0..f8 in order.
+template <typename T>
+__device__ __forceinline__ void d2q9_moments(const T (&f)[9], T &rho, T &ux, T &uy)
+{
+    rho = rn_add(rn_add(rn_add(rn_add(rn_add(rn_add(rn_add(rn_add(f[0], f[1]), f[2]), f[3]), f[4]), f[5]), f[6]), f[7]), f[8]);
+    const T sx = rn_add(rn_sub(rn_sub(rn_add(rn_sub(f[1], f[3]), f[5]), f[6]), f[7]), f[8]);
+    const T sy = rn_sub(rn_sub(rn_add(rn_add(rn_sub(f[2], f[4]), f[5]), f[6]), f[7]), f[8]);
+    ux = rn_div(sx, rho);
+    uy = rn_div(sy, rho);
+}
+
+}  // namespace lbm

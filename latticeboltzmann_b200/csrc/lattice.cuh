@@ -1,0 +1,64 @@
+// Device-side data model of one lattice block (shared by the kernels and the C ABI).
+//
+// HBM layout.  One cudaMalloc per block:
+//
+//     [ buffer A | buffer B | DevState ]
+//
+// Each buffer is a structure of arrays f[9][lnx + 2][pitch] in the reference's
+// index order (channel, x = k, y = l; y fastest -- cavity_opt2.py:79-83):
+//
+//     element(i, k, l) = i * pop_stride + (k + 1) * pitch + (l + PAD_L)
+//
+// with k in [-1, lnx] and l in [-1, lny]: one ghost row / column on every side,
+// ALWAYS present (a single block closes the periodic ring on itself).  PAD_L
+// puts cell l = 0 on a 128-byte boundary and `pitch` is a multiple of 128 bytes,
+// so every row of every population starts line-aligned and all stores of the
+// pull scheme are aligned.
+#pragma once
+#include <stdint.h>
+
+namespace lbm {
+
+constexpr int PAD_L = 32;          // elements before l = 0 in a row (128 B for f32, 256 B for f64)
+constexpr int TILE_L = 256;        // threads per CTA = cells of one row handled by a CTA
+constexpr int NUM_DIRS = 8;
+
+// (dx, dy) of direction slot d (include/lbm_b200.h).
+__host__ __device__ constexpr int dir_dx(int d) { return d == 0 || d == 4 || d == 5 ? -1 : (d == 1 || d == 6 || d == 7 ? 1 : 0); }
+__host__ __device__ constexpr int dir_dy(int d) { return d == 2 || d == 4 || d == 6 ? -1 : (d == 3 || d == 5 || d == 7 ? 1 : 0); }
+__host__ __device__ constexpr int dir_opp(int d) { return d == 0 ? 1 : d == 1 ? 0 : d == 2 ? 3 : d == 3 ? 2 : d == 4 ? 7 : d == 7 ? 4 : d == 5 ? 6 : 5; }
+
+// Lives at the tail of the block's allocation so that neighbours (other
+// processes / GPUs) can post their "halo pushed" flags straight into it.
+struct DevState {
+    unsigned long long step;               // completed time steps (buffer parity = step & 1)
+    unsigned long long flag_in[NUM_DIRS];  // flag_in[d]: steps whose halos the neighbour in slot d has pushed
+    unsigned int edge_done;                // edge CTAs finished in the running launch
+    unsigned int all_done;                 // CTAs finished in the running launch
+    unsigned int error;                    // != 0: a halo flag wait timed out
+    unsigned int pad;
+};
+
+template <typename T>
+struct NbrView {
+    T *buf[2];                       // neighbour's buffers A / B (local, peer or IPC-mapped address)
+    unsigned long long *flag_in;     // neighbour's DevState::flag_in
+    long long pop_stride, pitch;
+    int lnx, lny;
+};
+
+template <typename T>
+struct StepParams {
+    T *buf[2];
+    DevState *st;
+    long long pop_stride, pitch;
+    long long x0, y0, gnx, gny;
+    int lnx, lny;
+    int tiles_l, tiles_k, rows_per_tile;
+    long long n_perimeter;   // cells on the block's perimeter
+    int n_rim_ctas;          // CTAs [0, n_rim_ctas) handle the perimeter
+    T omega, u_wall;
+    NbrView<T> nbr[NUM_DIRS];
+};
+
+}  // namespace lbm

@@ -1,0 +1,480 @@
+// C ABI of the device-resident lattice (include/lbm_b200.h, group (2)).
+#include <cuda_runtime.h>
+#include <unistd.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <utility>
+#include <vector>
+
+#include "../../include/lbm_b200.h"
+#include "api_common.h"
+#include "step_kernel.cuh"
+
+using namespace lbm;
+
+struct NbrHost {
+    bool connected = false;
+    char *base = nullptr;   // neighbour's allocation as addressable from this process/device
+    lb_export exp{};
+};
+
+struct lb_lattice {
+    lb_config cfg{};
+    size_t elem = 8;
+    char *base = nullptr;
+    size_t buf_bytes = 0, state_off = 0, total_bytes = 0;
+    long long pitch = 0, pop_stride = 0;
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    NbrHost nbr[LB_NUM_DIRS];
+    std::map<std::pair<int64_t, uint64_t>, char *> ipc_open;   // (pid, remote base) -> mapped base
+    int rows_per_tile = 8;
+    int64_t steps = 0;
+    int64_t launches = 0;
+    // shear probe
+    void *d_uyk = nullptr, *d_series = nullptr;
+    int64_t probe_capacity = 0, probe_l_local = -1, probe_step0 = 0;
+    // scratch for moments
+    void *d_mom = nullptr;
+};
+
+namespace {
+
+DevState *dev_state(lb_lattice *L) { return reinterpret_cast<DevState *>(L->base + L->state_off); }
+
+template <typename T>
+StepParams<T> make_params(lb_lattice *L)
+{
+    StepParams<T> p{};
+    p.buf[0] = reinterpret_cast<T *>(L->base);
+    p.buf[1] = reinterpret_cast<T *>(L->base + L->buf_bytes);
+    p.st = dev_state(L);
+    p.pop_stride = L->pop_stride;
+    p.pitch = L->pitch;
+    p.x0 = L->cfg.x0;
+    p.y0 = L->cfg.y0;
+    p.gnx = L->cfg.gnx;
+    p.gny = L->cfg.gny;
+    p.lnx = (int)L->cfg.lnx;
+    p.lny = (int)L->cfg.lny;
+    p.rows_per_tile = L->rows_per_tile;
+    p.tiles_l = (p.lny + TILE_L - 1) / TILE_L;
+    p.tiles_k = (p.lnx + p.rows_per_tile - 1) / p.rows_per_tile;
+    p.n_perimeter = (long long)p.lny + (p.lnx > 1 ? p.lny : 0) + (p.lny > 1 ? 2 : 1) * (long long)(p.lnx > 2 ? p.lnx - 2 : 0);
+    p.n_rim_ctas = (int)((p.n_perimeter + TILE_L - 1) / TILE_L);
+    p.omega = (T)L->cfg.omega;
+    p.u_wall = (T)L->cfg.u_wall;
+    for (int d = 0; d < LB_NUM_DIRS; ++d) {
+        const NbrHost &n = L->nbr[d];
+        if (!n.connected) continue;
+        p.nbr[d].buf[0] = reinterpret_cast<T *>(n.base);
+        p.nbr[d].buf[1] = reinterpret_cast<T *>(n.base + n.exp.buf_bytes);
+        p.nbr[d].flag_in = reinterpret_cast<DevState *>(n.base + n.exp.state_offset)->flag_in;
+        p.nbr[d].pop_stride = n.exp.pop_stride;
+        p.nbr[d].pitch = n.exp.pitch;
+        p.nbr[d].lnx = (int)n.exp.lnx;
+        p.nbr[d].lny = (int)n.exp.lny;
+    }
+    return p;
+}
+
+template <typename T, int BC, bool EXACT>
+int launch_step_bc(lb_lattice *L, const StepParams<T> &p, bool collide)
+{
+    const int grid = p.n_rim_ctas + p.tiles_l * p.tiles_k;
+    if (collide)
+        step_kernel<T, BC, EXACT, true><<<grid, TILE_L, 0, L->stream>>>(p);
+    else
+        step_kernel<T, BC, EXACT, false><<<grid, TILE_L, 0, L->stream>>>(p);
+    return 0;
+}
+
+template <typename T>
+int launch_step(lb_lattice *L, bool collide)
+{
+    const StepParams<T> p = make_params<T>(L);
+    const bool exact = L->cfg.arith == LB_ARITH_EXACT;
+    switch (L->cfg.boundary) {
+    case LB_PERIODIC:
+        return exact ? launch_step_bc<T, BC_PERIODIC, true>(L, p, collide) : launch_step_bc<T, BC_PERIODIC, false>(L, p, collide);
+    case LB_CAVITY:
+        return exact ? launch_step_bc<T, BC_CAVITY, true>(L, p, collide) : launch_step_bc<T, BC_CAVITY, false>(L, p, collide);
+    case LB_CAVITY_XPERIODIC:
+        return exact ? launch_step_bc<T, BC_CAVITY_XPERIODIC, true>(L, p, collide)
+                     : launch_step_bc<T, BC_CAVITY_XPERIODIC, false>(L, p, collide);
+    default:
+        return lbm_fail(LB_ERR_INVALID, "boundary mode %d is not implemented by the fused step", L->cfg.boundary);
+    }
+}
+
+int check_ready(lb_lattice *L)
+{
+    if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
+    for (int d = 0; d < LB_NUM_DIRS; ++d)
+        if (!L->nbr[d].connected) return lbm_fail(LB_ERR_STATE, "direction slot %d is not connected (lb_connect)", d);
+    return 0;
+}
+
+int grid_for(long long n, int block) { long long g = (n + block - 1) / block; return (int)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g)); }
+
+}  // namespace
+
+extern "C" {
+
+int lb_abi_version(void) { return LB_ABI_VERSION; }
+
+int lb_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+int lb_create(const lb_config *cfg, lb_lattice **out)
+{
+    if (!cfg || !out) return lbm_fail(LB_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (cfg->dtype != LB_F32 && cfg->dtype != LB_F64) return lbm_fail(LB_ERR_INVALID, "dtype must be LB_F32 or LB_F64");
+    if (cfg->lnx < 1 || cfg->lny < 1 || cfg->gnx < cfg->lnx || cfg->gny < cfg->lny || cfg->x0 < 0 || cfg->y0 < 0 ||
+        cfg->x0 + cfg->lnx > cfg->gnx || cfg->y0 + cfg->lny > cfg->gny)
+        return lbm_fail(LB_ERR_INVALID, "inconsistent block geometry");
+    if (cfg->lnx > (1ll << 30) || cfg->lny > (1ll << 30)) return lbm_fail(LB_ERR_INVALID, "block extent too large");
+    if (cfg->boundary < LB_PERIODIC || cfg->boundary > LB_SF_SLIDING_LID) return lbm_fail(LB_ERR_INVALID, "unknown boundary");
+    if (cfg->arith != LB_ARITH_EXACT && cfg->arith != LB_ARITH_FAST) return lbm_fail(LB_ERR_INVALID, "unknown arith");
+    // A wall-bounded box needs two distinct wall rows/columns: with a single row the reference's
+    // sequential overwrites (cavity_opt2.py:134-177) alias top and bottom and the gather form does not apply.
+    if (cfg->boundary != LB_PERIODIC && (cfg->gny < 2 || (cfg->boundary != LB_CAVITY_XPERIODIC && cfg->gnx < 2)))
+        return lbm_fail(LB_ERR_INVALID, "wall-bounded lattices need at least 2 cells across each walled direction");
+    if (lb_device_count() <= 0)
+        return lbm_fail(LB_ERR_NO_DEVICE, "no CUDA device visible: liblbm_b200 has no CPU fallback");
+    LBM_CUDA(cudaSetDevice(cfg->device));
+
+    lb_lattice *L = new lb_lattice();
+    L->cfg = *cfg;
+    L->elem = cfg->dtype == LB_F64 ? 8 : 4;
+    // pitch: multiple of 32 elements (>= 128 B), room for PAD_L, lny cells and the upper ghost column.
+    L->pitch = ((cfg->lny + PAD_L + 1 + 31) / 32) * 32;
+    L->pop_stride = (cfg->lnx + 2) * L->pitch;
+    L->buf_bytes = (size_t)9 * L->pop_stride * L->elem;
+    L->buf_bytes = (L->buf_bytes + 255) / 256 * 256;
+    L->state_off = 2 * L->buf_bytes;
+    L->total_bytes = L->state_off + 256;
+    cudaError_t e = cudaMalloc(&L->base, L->total_bytes);
+    if (e != cudaSuccess) {
+        delete L;
+        return lbm_fail(LB_ERR_CUDA, "cudaMalloc(%zu bytes): %s", (size_t)(2 * (size_t)9 * (cfg->lnx + 2) * ((cfg->lny + 64)) * 8), cudaGetErrorString(e));
+    }
+    LBM_CUDA(cudaStreamCreateWithFlags(&L->own_stream, cudaStreamNonBlocking));
+    L->stream = L->own_stream;
+    LBM_CUDA(cudaEventCreate(&L->ev0));
+    LBM_CUDA(cudaEventCreate(&L->ev1));
+    LBM_CUDA(cudaMemsetAsync(L->base, 0, L->total_bytes, L->stream));
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    const char *env = getenv("LBM_ROWS_PER_TILE");
+    if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
+    *out = L;
+    return 0;
+}
+
+int lb_destroy(lb_lattice *L)
+{
+    if (!L) return 0;
+    cudaSetDevice(L->cfg.device);
+    // L->stream may be borrowed (another block's or torch's) and already gone: sync the device.
+    cudaDeviceSynchronize();
+    for (auto &kv : L->ipc_open) cudaIpcCloseMemHandle(kv.second);
+    if (L->d_uyk) cudaFree(L->d_uyk);
+    if (L->d_series) cudaFree(L->d_series);
+    if (L->d_mom) cudaFree(L->d_mom);
+    if (L->ev0) cudaEventDestroy(L->ev0);
+    if (L->ev1) cudaEventDestroy(L->ev1);
+    if (L->own_stream) cudaStreamDestroy(L->own_stream);
+    if (L->base) cudaFree(L->base);
+    delete L;
+    return 0;
+}
+
+int lb_set_stream(lb_lattice *L, void *s)
+{
+    if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
+    L->stream = s ? reinterpret_cast<cudaStream_t>(s) : L->own_stream;
+    return 0;
+}
+
+void *lb_get_stream(lb_lattice *L) { return L ? reinterpret_cast<void *>(L->stream) : nullptr; }
+
+int lb_set_rows_per_tile(lb_lattice *L, int rows)
+{
+    if (!L || rows < 1) return lbm_fail(LB_ERR_INVALID, "rows_per_tile must be >= 1");
+    L->rows_per_tile = rows;
+    return 0;
+}
+
+int lb_sync(lb_lattice *L)
+{
+    if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    return 0;
+}
+
+int lb_get_export(lb_lattice *L, lb_export *out)
+{
+    if (!L || !out) return lbm_fail(LB_ERR_INVALID, "null argument");
+    memset(out, 0, sizeof(*out));
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    cudaIpcMemHandle_t h;
+    static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+    cudaError_t e = cudaIpcGetMemHandle(&h, L->base);
+    if (e == cudaSuccess)
+        memcpy(out->ipc_mem_handle, &h, 64);
+    else
+        cudaGetLastError();   // IPC unsupported here: same-process wiring still works
+    out->local_base = reinterpret_cast<uint64_t>(L->base);
+    out->pid = (int64_t)getpid();
+    out->device = L->cfg.device;
+    out->dtype = L->cfg.dtype;
+    out->lnx = L->cfg.lnx;
+    out->lny = L->cfg.lny;
+    out->pitch = L->pitch;
+    out->pop_stride = L->pop_stride;
+    out->buf_bytes = (int64_t)L->buf_bytes;
+    out->state_offset = (int64_t)L->state_off;
+    out->total_bytes = (int64_t)L->total_bytes;
+    return 0;
+}
+
+int lb_connect(lb_lattice *L, int dir, const lb_export *nb)
+{
+    if (!L || !nb || dir < 0 || dir >= LB_NUM_DIRS) return lbm_fail(LB_ERR_INVALID, "bad argument");
+    if (nb->dtype != L->cfg.dtype) return lbm_fail(LB_ERR_INVALID, "neighbour dtype differs");
+    // faces must match: x-neighbours share lny, y-neighbours share lnx
+    if (dir_dy(dir) == 0 && nb->lny != L->cfg.lny) return lbm_fail(LB_ERR_INVALID, "x-neighbour with different lny");
+    if (dir_dx(dir) == 0 && nb->lnx != L->cfg.lnx) return lbm_fail(LB_ERR_INVALID, "y-neighbour with different lnx");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    char *base = nullptr;
+    if (nb->pid == (int64_t)getpid()) {
+        base = reinterpret_cast<char *>(nb->local_base);
+        if (nb->device != L->cfg.device) {
+            int can = 0;
+            LBM_CUDA(cudaDeviceCanAccessPeer(&can, L->cfg.device, nb->device));
+            if (!can) return lbm_fail(LB_ERR_CUDA, "device %d cannot access peer %d", L->cfg.device, nb->device);
+            cudaError_t e = cudaDeviceEnablePeerAccess(nb->device, 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled)
+                return lbm_fail(LB_ERR_CUDA, "cudaDeviceEnablePeerAccess: %s", cudaGetErrorString(e));
+            cudaGetLastError();
+        }
+    } else {
+        auto key = std::make_pair(nb->pid, nb->local_base);
+        auto it = L->ipc_open.find(key);
+        if (it != L->ipc_open.end()) {
+            base = it->second;
+        } else {
+            cudaIpcMemHandle_t h;
+            memcpy(&h, nb->ipc_mem_handle, 64);
+            void *ptr = nullptr;
+            cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+            if (e != cudaSuccess) return lbm_fail(LB_ERR_CUDA, "cudaIpcOpenMemHandle(pid %lld): %s", (long long)nb->pid, cudaGetErrorString(e));
+            base = static_cast<char *>(ptr);
+            L->ipc_open[key] = base;
+        }
+    }
+    L->nbr[dir].connected = true;
+    L->nbr[dir].base = base;
+    L->nbr[dir].exp = *nb;
+    return 0;
+}
+
+int lb_halo_refresh(lb_lattice *L)
+{
+    if (int r = check_ready(L)) return r;
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    const long long n_rim = 2 * (L->cfg.lnx + L->cfg.lny);
+    if (L->cfg.dtype == LB_F64)
+        halo_refresh_kernel<double><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(make_params<double>(L));
+    else
+        halo_refresh_kernel<float><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(make_params<float>(L));
+    LBM_CUDA(cudaGetLastError());
+    L->launches++;
+    return 0;
+}
+
+static int copy_f(lb_lattice *L, void *host, bool upload)
+{
+    if (!L || !host) return lbm_fail(LB_ERR_INVALID, "null argument");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    const size_t e = L->elem;
+    char *cur = L->base + (L->steps & 1) * L->buf_bytes;
+    const size_t row = (size_t)L->cfg.lny * e;
+    for (int i = 0; i < 9; ++i) {
+        char *d = cur + ((size_t)i * L->pop_stride + (size_t)L->pitch + PAD_L) * e;
+        char *h = static_cast<char *>(host) + (size_t)i * L->cfg.lnx * row;
+        if (upload)
+            LBM_CUDA(cudaMemcpy2DAsync(d, (size_t)L->pitch * e, h, row, row, (size_t)L->cfg.lnx, cudaMemcpyHostToDevice, L->stream));
+        else
+            LBM_CUDA(cudaMemcpy2DAsync(h, row, d, (size_t)L->pitch * e, row, (size_t)L->cfg.lnx, cudaMemcpyDeviceToHost, L->stream));
+    }
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    return 0;
+}
+
+int lb_upload_f(lb_lattice *L, const void *host_f) { return copy_f(L, const_cast<void *>(host_f), true); }
+int lb_download_f(lb_lattice *L, void *host_f) { return copy_f(L, host_f, false); }
+
+int lb_init_equilibrium(lb_lattice *L, const void *rho, const void *ux, const void *uy)
+{
+    if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    const long long n = L->cfg.lnx * L->cfg.lny;
+    const size_t bytes = (size_t)n * L->elem;
+    void *d[3] = {nullptr, nullptr, nullptr};
+    const void *h[3] = {rho, ux, uy};
+    for (int j = 0; j < 3; ++j)
+        if (h[j]) {
+            LBM_CUDA(cudaMalloc(&d[j], bytes));
+            LBM_CUDA(cudaMemcpyAsync(d[j], h[j], bytes, cudaMemcpyHostToDevice, L->stream));
+        }
+    if (L->cfg.dtype == LB_F64)
+        init_equilibrium_kernel<double><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<double>(L), (const double *)d[0], (const double *)d[1], (const double *)d[2]);
+    else
+        init_equilibrium_kernel<float><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<float>(L), (const float *)d[0], (const float *)d[1], (const float *)d[2]);
+    LBM_CUDA(cudaGetLastError());
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    for (int j = 0; j < 3; ++j)
+        if (d[j]) cudaFree(d[j]);
+    L->launches++;
+    return 0;
+}
+
+int lb_step(lb_lattice *L, int64_t nsteps)
+{
+    if (int r = check_ready(L)) return r;
+    if (nsteps < 0) return lbm_fail(LB_ERR_INVALID, "nsteps < 0");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    for (int64_t s = 0; s < nsteps; ++s) {
+        int r = L->cfg.dtype == LB_F64 ? launch_step<double>(L, true) : launch_step<float>(L, true);
+        if (r) return r;
+        L->launches++;
+        L->steps++;
+        if (L->d_series) {
+            if (L->cfg.dtype == LB_F64)
+                shear_probe_kernel<double><<<1, 256, 0, L->stream>>>(make_params<double>(L), (int)L->probe_l_local, (const double *)L->d_uyk,
+                                                                      (double *)L->d_series, L->probe_capacity, (unsigned long long)L->probe_step0);
+            else
+                shear_probe_kernel<float><<<1, 256, 0, L->stream>>>(make_params<float>(L), (int)L->probe_l_local, (const float *)L->d_uyk,
+                                                                     (float *)L->d_series, L->probe_capacity, (unsigned long long)L->probe_step0);
+            L->launches++;
+        }
+    }
+    LBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* Stream + boundary handling only (no collision): PyLB.stream /
+ * stream_and_bounce_back as a stand-alone operation (cavity_opt2.py:109-177). */
+int lb_stream_only(lb_lattice *L, int64_t nsteps)
+{
+    if (int r = check_ready(L)) return r;
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    for (int64_t s = 0; s < nsteps; ++s) {
+        int r = L->cfg.dtype == LB_F64 ? launch_step<double>(L, false) : launch_step<float>(L, false);
+        if (r) return r;
+        L->launches++;
+        L->steps++;
+    }
+    LBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+int lb_step_timed(lb_lattice *L, int64_t nsteps, float *ms)
+{
+    if (!L || !ms) return lbm_fail(LB_ERR_INVALID, "null argument");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_CUDA(cudaEventRecord(L->ev0, L->stream));
+    if (int r = lb_step(L, nsteps)) return r;
+    LBM_CUDA(cudaEventRecord(L->ev1, L->stream));
+    LBM_CUDA(cudaEventSynchronize(L->ev1));
+    LBM_CUDA(cudaEventElapsedTime(ms, L->ev0, L->ev1));
+    return 0;
+}
+
+int64_t lb_steps_done(lb_lattice *L) { return L ? L->steps : -1; }
+
+int lb_health(lb_lattice *L)
+{
+    if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    DevState h;
+    LBM_CUDA(cudaMemcpy(&h, dev_state(L), sizeof(h), cudaMemcpyDeviceToHost));
+    if (h.error) return lbm_fail(LB_ERR_HALO_TIMEOUT, "halo flag wait timed out inside the step kernel");
+    if ((int64_t)h.step != L->steps)
+        return lbm_fail(LB_ERR_STATE, "device step counter %llu != host %lld", h.step, (long long)L->steps);
+    return 0;
+}
+
+int lb_moments(lb_lattice *L, void *rho, void *ux, void *uy)
+{
+    if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    const long long n = L->cfg.lnx * L->cfg.lny;
+    const size_t bytes = (size_t)n * L->elem;
+    if (!L->d_mom) LBM_CUDA(cudaMalloc(&L->d_mom, 3 * bytes));
+    char *d = static_cast<char *>(L->d_mom);
+    if (L->cfg.dtype == LB_F64)
+        moments_kernel<double><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<double>(L), (double *)d, (double *)(d + bytes), (double *)(d + 2 * bytes));
+    else
+        moments_kernel<float><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<float>(L), (float *)d, (float *)(d + bytes), (float *)(d + 2 * bytes));
+    LBM_CUDA(cudaGetLastError());
+    L->launches++;
+    void *h[3] = {rho, ux, uy};
+    for (int j = 0; j < 3; ++j)
+        if (h[j]) LBM_CUDA(cudaMemcpyAsync(h[j], d + j * bytes, bytes, cudaMemcpyDeviceToHost, L->stream));
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    return 0;
+}
+
+int lb_probe_shear_enable(lb_lattice *L, int64_t l_global, const void *uy_k, int64_t capacity)
+{
+    if (!L || !uy_k || capacity < 1) return lbm_fail(LB_ERR_INVALID, "bad argument");
+    const int64_t l_local = l_global - L->cfg.y0;
+    if (l_local < 0 || l_local >= L->cfg.lny) return lbm_fail(LB_ERR_INVALID, "probe row is not inside this block");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    if (L->d_uyk) cudaFree(L->d_uyk);
+    if (L->d_series) cudaFree(L->d_series);
+    LBM_CUDA(cudaMalloc(&L->d_uyk, (size_t)L->cfg.lnx * L->elem));
+    LBM_CUDA(cudaMalloc(&L->d_series, (size_t)capacity * L->elem));
+    LBM_CUDA(cudaMemcpy(L->d_uyk, uy_k, (size_t)L->cfg.lnx * L->elem, cudaMemcpyHostToDevice));
+    LBM_CUDA(cudaMemset(L->d_series, 0, (size_t)capacity * L->elem));
+    L->probe_capacity = capacity;
+    L->probe_l_local = l_local;
+    L->probe_step0 = L->steps;
+    return 0;
+}
+
+int lb_probe_shear_read(lb_lattice *L, void *out, int64_t n)
+{
+    if (!L || !out || !L->d_series || n > L->probe_capacity) return lbm_fail(LB_ERR_INVALID, "bad argument");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    LBM_CUDA(cudaMemcpy(out, L->d_series, (size_t)n * L->elem, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+int64_t lb_pitch(lb_lattice *L) { return L ? L->pitch : -1; }
+int64_t lb_pop_stride(lb_lattice *L) { return L ? L->pop_stride : -1; }
+int lb_kernel_launches(lb_lattice *L, int64_t *count)
+{
+    if (!L || !count) return lbm_fail(LB_ERR_INVALID, "null argument");
+    *count = L->launches;
+    return 0;
+}
+
+}  // extern "C"

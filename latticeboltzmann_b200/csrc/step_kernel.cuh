@@ -1,0 +1,330 @@
+// The fused D2Q9 time step: pull-stream + boundary handling + BGK collide +
+// halo push into the neighbours' ghost layers, ONE kernel launch per step.
+//
+// Replaces, per step (cavity_opt2.py:272-277):
+//   communicate()            cavity_opt2.py:179-210  (4 blocking MPI Sendrecv)
+//   stream_and_bounce_back() cavity_opt2.py:109-177  (8 np.roll + ~30 slice stores)
+//   D2Q9.collide()           c/d2q9.h:121-131        (serial C++ loop)
+//
+// Scheme: post[i,k,l] = pre[i,k-cx,l-cy] read from buffer
+// `step & 1`, boundary predicates on GLOBAL coordinates, collide in registers,
+// write buffer `(step+1) & 1`.  Every block always owns a one-cell ghost frame;
+// cells on the block's rim additionally store the 3 (faces) / 1 (corners)
+// populations that leave the block straight into the neighbour's ghost frame
+// -- local memory for a self-closed periodic ring, a peer-mapped NVLink address
+// for another GPU.  Interior cells therefore never test for wrap-around.
+//
+// Cross-block ordering uses one monotonically increasing flag per direction
+// (DevState::flag_in).  Step n's rim CTAs first wait until all 8 neighbours have
+// posted `n` (their step n-1 halos are in my ghosts AND they are done reading
+// the ghosts I am about to overwrite), and the last rim CTA to finish posts
+// `n+1` to all 8 neighbours.  "Rim" CTAs own exactly the block's perimeter cells
+// (the only cells that read ghosts, see a wall, or push halos); they take the
+// lowest block indices so they are scheduled first and the interior update --
+// predicate-free tiles of rows_per_tile x 256 cells -- overlaps the exchange.
+#pragma once
+#include "d2q9_math.cuh"
+#include "lattice.cuh"
+
+namespace lbm {
+
+enum BoundaryKind { BC_PERIODIC = 0, BC_CAVITY = 1, BC_CAVITY_XPERIODIC = 2 };
+
+constexpr unsigned long long HALO_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// Loads: rim tiles read ghost cells that a peer may have written during this
+// launch's lifetime, so they bypass the (non-coherent) L1.
+template <bool RIM, typename T>
+__device__ __forceinline__ T ld_f(const T *p)
+{
+    if (RIM) return __ldcg(p);
+    return *p;
+}
+
+// Perimeter cell t of the block -> (k, l).  Segments: row k=0, row k=lnx-1,
+// column l=0 (k in 1..lnx-2), column l=lny-1 (k in 1..lnx-2).
+template <typename T>
+__device__ __forceinline__ void decode_perimeter(const StepParams<T> &p, long long t, int &k, int &l)
+{
+    const long long a = p.lny, b = (p.lnx > 1) ? p.lny : 0, c = (p.lnx > 2) ? p.lnx - 2 : 0;
+    if (t < a) { k = 0; l = (int)t; }
+    else if (t < a + b) { k = p.lnx - 1; l = (int)(t - a); }
+    else if (t < a + b + c) { k = 1 + (int)(t - a - b); l = 0; }
+    else { k = 1 + (int)(t - a - b - c); l = p.lny - 1; }
+}
+
+// Store the populations that leave the block through cell (k, l) into the
+// neighbours' ghost frames of buffer `par`.
+template <typename T>
+__device__ __forceinline__ void push_halo(const StepParams<T> &p, int par, int k, int l, const T (&f)[9])
+{
+    const bool xl = (k == 0), xh = (k == p.lnx - 1), yl = (l == 0), yh = (l == p.lny - 1);
+    if (!(xl | xh | yl | yh)) return;
+#define LBM_PUSH(D, KK, LL, I)                                                              \
+    do {                                                                                    \
+        const NbrView<T> &nb = p.nbr[D];                                                    \
+        nb.buf[par][(long long)(I) * nb.pop_stride + (long long)((KK) + 1) * nb.pitch + ((LL) + PAD_L)] = f[I]; \
+    } while (0)
+    if (xh) {   // +x face -> ghost row -1 of the right neighbour: E, NE, SE
+        LBM_PUSH(1, -1, l, QE);
+        LBM_PUSH(1, -1, l, QNE);
+        LBM_PUSH(1, -1, l, QSE);
+    }
+    if (xl) {   // -x face -> ghost row lnx of the left neighbour: W, NW, SW
+        LBM_PUSH(0, p.nbr[0].lnx, l, QW);
+        LBM_PUSH(0, p.nbr[0].lnx, l, QNW);
+        LBM_PUSH(0, p.nbr[0].lnx, l, QSW);
+    }
+    if (yh) {   // +y face -> ghost column -1 of the upper neighbour: N, NE, NW
+        LBM_PUSH(3, k, -1, QN);
+        LBM_PUSH(3, k, -1, QNE);
+        LBM_PUSH(3, k, -1, QNW);
+    }
+    if (yl) {   // -y face -> ghost column lny of the lower neighbour: S, SW, SE
+        LBM_PUSH(2, k, p.nbr[2].lny, QS);
+        LBM_PUSH(2, k, p.nbr[2].lny, QSW);
+        LBM_PUSH(2, k, p.nbr[2].lny, QSE);
+    }
+    if (xh && yh) LBM_PUSH(7, -1, -1, QNE);
+    if (xh && yl) LBM_PUSH(6, -1, p.nbr[6].lny, QSE);
+    if (xl && yh) LBM_PUSH(5, p.nbr[5].lnx, -1, QNW);
+    if (xl && yl) LBM_PUSH(4, p.nbr[4].lnx, p.nbr[4].lny, QSW);
+#undef LBM_PUSH
+}
+
+// One cell: gather, boundary rules, collide, store (+ halo push on rim tiles).
+template <typename T, int BC, bool EXACT, bool COLLIDE, bool RIM>
+__device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__restrict__ src, T *__restrict__ dst,
+                                            int par_dst, int k, int l)
+{
+    const long long S = p.pop_stride, P = p.pitch;
+    const long long c = (long long)(k + 1) * P + (l + PAD_L);
+    T f[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = ld_f<RIM>(src + i * S + c - cx_of(i) * P - cy_of(i));
+
+    if (RIM && BC != BC_PERIODIC) {
+        // SURVEY.md App. A.2 == cavity_opt2.py:133-177 as a gather.  Predicates on
+        // global coordinates; the wall sits half a cell outside the lattice.
+        const long long gk = p.x0 + k, gl = p.y0 + l;
+        const bool walls = (BC == BC_CAVITY);
+        const bool bottom = (gl == 0), top = (gl == p.gny - 1);
+        const bool left = walls && (gk == 0), right = walls && (gk == p.gnx - 1);
+        if (bottom | top | left | right) {
+            T lid = T(0), o_nw = T(0), o_ne = T(0);
+            if (top) {
+                // cavity_opt2.py:140-142: rho from 3 pre-stream + 6 streamed (periodically
+                // rolled, pre-wall-overwrite) populations, summed left to right.
+                o_nw = ld_f<true>(src + QNW * S + c);
+                o_ne = ld_f<true>(src + QNE * S + c);
+                T rho = rn_add(o_nw, ld_f<true>(src + QN * S + c));
+                rho = rn_add(rho, o_ne);
+                rho = rn_add(rho, f[QNW]);
+                rho = rn_add(rho, f[QN]);
+                rho = rn_add(rho, f[QNE]);
+                rho = rn_add(rho, f[QW]);
+                rho = rn_add(rho, f[Q0]);
+                rho = rn_add(rho, f[QE]);
+                // 6*w_i[D.SE]*rho*u0 (:144-145): w = fp(1/36) rounded to T, 6*w rounded in T.
+                const T six_w = rn_mul(T(6), T(1.0 / 36.0));
+                lid = rn_mul(rn_mul(six_w, rho), p.u_wall);
+            }
+            // half-way bounce-back: a population whose source cell lies outside the box is
+            // replaced by the cell's own opposite pre-stream population (:134-136,:150-177).
+#pragma unroll
+            for (int i = 1; i < 9; ++i) {
+                const bool outside = (cy_of(i) == 1 && bottom) || (cy_of(i) == -1 && top) ||
+                                     (cx_of(i) == 1 && left) || (cx_of(i) == -1 && right);
+                if (outside) f[i] = ld_f<true>(src + opp_of(i) * S + c);
+            }
+            if (top) {
+                if (!left) f[QSE] = rn_add(o_nw, lid);    // :144, overridden by the left wall at k=0 (:152,:172)
+                if (!right) f[QSW] = rn_sub(o_ne, lid);   // :145, overridden by the right wall at k=X (:157,:177)
+            }
+        }
+    }
+
+    if (COLLIDE) d2q9_collide<T, EXACT>(f, p.omega);
+
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dst[i * S + c] = f[i];
+    if (RIM) push_halo<T>(p, par_dst, k, l, f);
+}
+
+// Resident CTAs per SM the register allocation is tuned for (x 256 threads).
+template <typename T, bool EXACT>
+__host__ __device__ constexpr int min_ctas_per_sm() { return (sizeof(T) == 8 && EXACT) ? 3 : 4; }
+
+template <typename T, int BC, bool EXACT, bool COLLIDE>
+__global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kernel(const __grid_constant__ StepParams<T> p)
+{
+    DevState *st = p.st;
+    const unsigned long long step = *(volatile unsigned long long *)&st->step;
+    const int par = (int)(step & 1ull);
+    const T *__restrict__ src = p.buf[par];
+    T *__restrict__ dst = p.buf[par ^ 1];
+
+    if ((int)blockIdx.x < p.n_rim_ctas) {
+        // ---- rim CTAs: the block's perimeter cells, ghost reads, halo pushes ----
+        // Wait for the 8 neighbours' step-(n-1) halos (and for them to be done
+        // reading the ghosts this step overwrites).
+        if (threadIdx.x < NUM_DIRS) {
+            if (*(volatile unsigned int *)&st->error == 0) {
+                const unsigned long long t0 = global_timer_ns();
+                while (ld_acquire_sys(&st->flag_in[threadIdx.x]) < step) {
+                    if (global_timer_ns() - t0 > HALO_TIMEOUT_NS) {
+                        atomicExch(&st->error, 1u);
+                        break;
+                    }
+                }
+            }
+        }
+        __syncthreads();
+        const long long t = (long long)blockIdx.x * TILE_L + threadIdx.x;
+        if (t < p.n_perimeter) {
+            int k, l;
+            decode_perimeter<T>(p, t, k, l);
+            update_cell<T, BC, EXACT, COLLIDE, true>(p, src, dst, par ^ 1, k, l);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned int prev = atomicAdd(&st->edge_done, 1u);
+            if (prev == (unsigned int)p.n_rim_ctas - 1u) {
+                st->edge_done = 0u;
+                __threadfence_system();
+#pragma unroll
+                for (int d = 0; d < NUM_DIRS; ++d) st_release_sys(p.nbr[d].flag_in + dir_opp(d), step + 1ull);
+            }
+        }
+    } else {
+        // ---- interior CTAs: rows_per_tile x 256 cells, no ghosts, no predicates ----
+        const int tile = (int)blockIdx.x - p.n_rim_ctas;
+        const int kt = tile / p.tiles_l, lt = tile - kt * p.tiles_l;
+        const int l = lt * TILE_L + threadIdx.x;
+        const int k0 = max(kt * p.rows_per_tile, 1);
+        const int k1 = min(kt * p.rows_per_tile + p.rows_per_tile, p.lnx - 1);
+        if (l >= 1 && l < p.lny - 1) {
+#pragma unroll 1
+            for (int k = k0; k < k1; ++k) update_cell<T, BC, EXACT, COLLIDE, false>(p, src, dst, par ^ 1, k, l);
+        }
+        __syncthreads();
+    }
+    // The last CTA of the launch publishes the new step count (read by the next
+    // launch -- which makes the launch arguments step-independent and the whole
+    // loop CUDA-graph replayable).
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&st->all_done, 1u);
+        if (prev == gridDim.x - 1u) {
+            st->all_done = 0u;
+            *(volatile unsigned long long *)&st->step = step + 1ull;
+        }
+    }
+}
+
+// Push the rim of the CURRENT buffer (used once after init / upload).
+template <typename T>
+__global__ void halo_refresh_kernel(const __grid_constant__ StepParams<T> p)
+{
+    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    const T *src = p.buf[par];
+    const long long n_rim = 2ll * p.lnx + 2ll * p.lny;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_rim; t += (long long)gridDim.x * blockDim.x) {
+        int k, l;
+        if (t < p.lny) { k = 0; l = (int)t; }
+        else if (t < 2ll * p.lny) { k = p.lnx - 1; l = (int)(t - p.lny); }
+        else if (t < 2ll * p.lny + p.lnx) { k = (int)(t - 2ll * p.lny); l = 0; }
+        else { k = (int)(t - 2ll * p.lny - p.lnx); l = p.lny - 1; }
+        T f[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = __ldcg(src + i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L));
+        push_halo<T>(p, par, k, l, f);
+    }
+}
+
+// f = feq(rho, ux, uy) on the real cells of the current buffer (c/d2q9.h:98-108).
+template <typename T>
+__global__ void init_equilibrium_kernel(const __grid_constant__ StepParams<T> p, const T *__restrict__ rho,
+                                        const T *__restrict__ ux, const T *__restrict__ uy)
+{
+    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    T *dst = p.buf[par];
+    const long long n = (long long)p.lnx * p.lny;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / p.lny), l = (int)(t % p.lny);
+        T e[9];
+        d2q9_equilibrium<T, true>(rho ? rho[t] : T(1), ux ? ux[t] : T(0), uy ? uy[t] : T(0), e);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dst[i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L)] = e[i];
+    }
+}
+
+// rho, ux, uy of the current buffer into dense (lnx, lny) arrays (cavity_opt2.py:280-281).
+template <typename T>
+__global__ void moments_kernel(const __grid_constant__ StepParams<T> p, T *__restrict__ rho, T *__restrict__ ux,
+                               T *__restrict__ uy)
+{
+    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    const T *src = p.buf[par];
+    const long long n = (long long)p.lnx * p.lny;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / p.lny), l = (int)(t % p.lny);
+        T f[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = src[i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L)];
+        T r, x, y;
+        d2q9_moments<T>(f, r, x, y);
+        if (rho) rho[t] = r;
+        if (ux) ux[t] = x;
+        if (uy) uy[t] = y;
+    }
+}
+
+// shear_wave_opt2.py:99 -- one block; deterministic tree reduction.
+template <typename T>
+__global__ void shear_probe_kernel(const __grid_constant__ StepParams<T> p, int l_local, const T *__restrict__ uy_k,
+                                   T *__restrict__ series, long long capacity, unsigned long long step0)
+{
+    __shared__ T red[256];
+    const unsigned long long step = *(volatile unsigned long long *)&p.st->step;
+    const int par = (int)(step & 1ull);
+    const T *src = p.buf[par];
+    T acc = T(0);
+    for (int k = threadIdx.x; k < p.lnx; k += blockDim.x) {
+        T f[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = src[i * p.pop_stride + (long long)(k + 1) * p.pitch + (l_local + PAD_L)];
+        T r, x, y;
+        d2q9_moments<T>(f, r, x, y);
+        acc += y * uy_k[k];
+    }
+    red[threadIdx.x] = acc;
+    __syncthreads();
+    for (int s = blockDim.x / 2; s > 0; s >>= 1) {
+        if ((int)threadIdx.x < s) red[threadIdx.x] += red[threadIdx.x + s];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        const long long idx = (long long)(step - step0) - 1;
+        if (idx >= 0 && idx < capacity) series[idx] = red[0] * T(2) / T(p.gnx);
+    }
+}
+
+}  // namespace lbm
