@@ -31,11 +31,26 @@ __host__ __device__ constexpr int opp_of(int i) { return i == 0 ? 0 : (i <= 4 ? 
 __device__ __forceinline__ double rn_add(double a, double b) { return __dadd_rn(a, b); }
 __device__ __forceinline__ double rn_sub(double a, double b) { return __dsub_rn(a, b); }
 __device__ __forceinline__ double rn_mul(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ double rn_div(double a, double b) { return __ddiv_rn(a, b); }
+// IEEE division.  nvcc's inline fast path (MUFU.RCP64H + 2 Newton steps + Markstein correction, ~12
+// instructions) bails out to a ~100-instruction subroutine when the numerator is zero or tiny -- and a
+// fluid at rest has ux = uy = uu = 0 EXACTLY in every cell, so a cavity spends most of its time there.
+// 0/b is +-0 with sign(a)^sign(b); b is a density or a positive constant here, never 0/inf/nan... if it
+// were, the general path below still handles it because only a == 0 with finite non-zero b is shortcut.
+__device__ __forceinline__ double rn_div(double a, double b)
+{
+    if (a == 0.0 && b == b && fabs(b) <= 1.79769313486231570e308 && b != 0.0)
+        return __longlong_as_double((__double_as_longlong(a) ^ __double_as_longlong(b)) & (long long)0x8000000000000000ull);
+    return __ddiv_rn(a, b);
+}
 __device__ __forceinline__ float rn_add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float rn_sub(float a, float b) { return __fsub_rn(a, b); }
 __device__ __forceinline__ float rn_mul(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ float rn_div(float a, float b) { return __fdiv_rn(a, b); }
+__device__ __forceinline__ float rn_div(float a, float b)
+{
+    if (a == 0.0f && b == b && fabsf(b) <= 3.402823466e38f && b != 0.0f)
+        return __int_as_float((__float_as_int(a) ^ __float_as_int(b)) & (int)0x80000000u);
+    return __fdiv_rn(a, b);
+}
 
 // c/d2q9.h:59-81
 template <typename T, bool EXACT>

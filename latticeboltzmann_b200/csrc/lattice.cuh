@@ -58,6 +58,10 @@ struct StepParams {
     long long n_perimeter;   // cells on the block's perimeter
     int n_rim_ctas;          // CTAs [0, n_rim_ctas) handle the perimeter
     T omega, u_wall;
+    // Byte offsets relative to a cell's own slot, precomputed on the host so that the kernel adds
+    // them straight from the constant bank (no registers): ld_off[i] addresses the pull source
+    // (i, k - cx_i, l - cy_i).
+    long long ld_off[9];
     NbrView<T> nbr[NUM_DIRS];
 };
 

@@ -68,6 +68,9 @@ StepParams<T> make_params(lb_lattice *L)
     p.n_rim_ctas = (int)((p.n_perimeter + TILE_L - 1) / TILE_L);
     p.omega = (T)L->cfg.omega;
     p.u_wall = (T)L->cfg.u_wall;
+    for (int i = 0; i < 9; ++i) {
+        p.ld_off[i] = (long long)sizeof(T) * (i * L->pop_stride - cx_of(i) * L->pitch - cy_of(i));
+    }
     for (int d = 0; d < LB_NUM_DIRS; ++d) {
         const NbrHost &n = L->nbr[d];
         if (!n.connected) continue;

@@ -116,9 +116,10 @@ __device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__r
 {
     const long long S = p.pop_stride, P = p.pitch;
     const long long c = (long long)(k + 1) * P + (l + PAD_L);
+    const char *sp = reinterpret_cast<const char *>(src + c);
     T f[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) f[i] = ld_f<RIM>(src + i * S + c - cx_of(i) * P - cy_of(i));
+    for (int i = 0; i < 9; ++i) f[i] = ld_f<RIM>(reinterpret_cast<const T *>(sp + p.ld_off[i]));
 
     if (RIM && BC != BC_PERIODIC) {
         // SURVEY.md App. A.2 == cavity_opt2.py:133-177 as a gather.  Predicates on
@@ -163,8 +164,13 @@ __device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__r
 
     if (COLLIDE) d2q9_collide<T, EXACT>(f, p.omega);
 
+    // stores walk the populations with one stride (a 9-entry offset table would be hoisted into 18 registers)
+    T *dp = dst + c;
 #pragma unroll
-    for (int i = 0; i < 9; ++i) dst[i * S + c] = f[i];
+    for (int i = 0; i < 9; ++i) {
+        *dp = f[i];
+        dp += S;
+    }
     if (RIM) push_halo<T>(p, par_dst, k, l, f);
 }
 

@@ -1,0 +1,77 @@
+"""world_size-2 gloo tests (CPU) of the multi-rank host logic: rendezvous, export
+exchange, periodic neighbour rings, scatter/gather -- checked bitwise against the
+single-rank oracle (the same gate the GPU path has to meet: 1 rank == N ranks)."""
+import os
+import socket
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from latticeboltzmann_b200.decomposition import Decomposition, axis_extents
+from oracle import oracle as orc
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def run_world(tmp_path, boundary, ndx, ndy, nx, ny, nsteps):
+    world = ndx * ndy
+    port = free_port()
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r),
+                   MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(HERE, "dist_worker.py"), str(tmp_path), boundary,
+                                       str(ndx), str(ndy), str(nx), str(ny), str(nsteps)], env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=240)
+        assert p.returncode == 0, out
+    return np.load(os.path.join(tmp_path, "gathered.npy"))
+
+
+@pytest.mark.parametrize("boundary,ndx,ndy", [("cavity", 2, 1), ("cavity", 1, 2), ("periodic", 2, 1)])
+def test_two_ranks_equal_single_rank_oracle(tmp_path, boundary, ndx, ndy):
+    nx, ny, nsteps = 13, 10, 6
+    got = run_world(tmp_path, boundary, ndx, ndy, nx, ny, nsteps)
+    ref = orc.perturbed_state(nx, ny, seed=21)
+    if boundary == "periodic":
+        orc.periodic_run(ref, 1.7, nsteps)
+    else:
+        orc.cavity_run(ref, 1.7, nsteps)
+    assert np.array_equal(got, ref)
+
+
+def test_axis_extents_follow_reference_remainder_rule():
+    # cavity_opt2.py:231-239: base = n // nd, the last block takes the remainder
+    assert axis_extents(10, 3) == [(0, 3), (3, 3), (6, 4)]
+    assert axis_extents(32768, 8)[-1] == (28672, 4096)
+    assert axis_extents(7, 1) == [(0, 7)]
+    with pytest.raises(ValueError):
+        axis_extents(2, 3)
+
+
+def test_decomposition_rank_layout_and_rings():
+    d = Decomposition(100, 60, 4, 2)
+    # Create_cart row-major numbering (cavity_opt2.py:225): rank = px*ndy + py
+    assert d.coords(5) == (2, 1) and d.rank_of(2, 1) == 5
+    # periodic rings: the left neighbour of px=0 is px=ndx-1
+    assert d.neighbour(0, 0) == d.rank_of(3, 0)
+    assert d.neighbour(7, 1) == d.rank_of(0, 1)
+    assert d.neighbour(0, 4) == d.rank_of(3, 1)      # (-1,-1) wraps in both directions
+    cover = np.zeros((100, 60), int)
+    for r in range(d.size):
+        sx, sy = d.slices(r)
+        cover[sx, sy] += 1
+    assert (cover == 1).all()
+    one = Decomposition(9, 9, 1, 1)
+    assert one.neighbours(0) == [0] * 8

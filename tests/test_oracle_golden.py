@@ -172,3 +172,16 @@ def test_simple_flows_sliding_lid_bitexact(golden_dir):
         sf.sliding_lid_step(f, float(g["omega"]), float(g["uw"]))
         if "f_%d" % (s + 1) in g:
             assert np.array_equal(f, g["f_%d" % (s + 1)]), s
+
+
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+def test_opt2_numpy_structure_bitexact(golden_dir, dt):
+    """The numpy-structured step bench.py times as the CPU baseline == the reference's function."""
+    from oracle import opt2_numpy
+    g = load(golden_dir, "cavity_opt2_bb_%s.npz" % dt)
+    for tag in "abcde":
+        f = g["in_" + tag].copy()
+        opt2_numpy.stream_and_bounce_back(f, float(g["u0_" + tag]))
+        assert np.array_equal(f, g["out_" + tag]), tag
+    t = opt2_numpy.run_independent_blocks(2, 32, 32, 1.7, 1, 2)
+    assert t > 0
