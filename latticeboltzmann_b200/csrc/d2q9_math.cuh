@@ -125,6 +125,55 @@ __device__ __forceinline__ void d2q9_collide(T (&f)[9], T omega)
     }
 }
 
+// ---- simple_flows flavour -------------------------------------------------
+// simulators/simple_flows/PoiseuilleFlow.py:25-42 (== slidingLid.py:33-50): a different algebraic
+// form of the same equilibrium.  numpy evaluates every operation separately in double, left to
+// right, so individually rounded operations in the same order are bit-identical.  2*rho/9, rho/18
+// and rho/36 are exact power-of-two multiples of rho/9 (one IEEE division instead of three).
+template <typename T>
+__device__ __forceinline__ void sf_equilibrium(T rho, T ux, T uy, T (&e)[9])
+{
+    const T p3 = rn_mul(T(3), rn_add(ux, uy));
+    const T m3 = rn_mul(T(3), rn_sub(ux, uy));
+    const T uu = rn_mul(T(3), rn_add(rn_mul(ux, ux), rn_mul(uy, uy)));
+    const T ux6 = rn_mul(T(6), ux), uy6 = rn_mul(T(6), uy);
+    const T uxx9 = rn_mul(rn_mul(T(9), ux), ux);
+    const T uyy9 = rn_mul(rn_mul(T(9), uy), uy);
+    const T uxy9 = rn_mul(rn_mul(T(9), ux), uy);
+    const T r9 = rn_div(rho, T(9));
+    const T a = rn_mul(T(2), r9), b = rn_mul(T(0.5), r9), c = rn_mul(T(0.25), r9);
+    e[0] = rn_mul(a, rn_sub(T(2), uu));
+    e[1] = rn_mul(b, rn_sub(rn_add(rn_add(T(2), ux6), uxx9), uu));
+    e[2] = rn_mul(b, rn_sub(rn_add(rn_add(T(2), uy6), uyy9), uu));
+    e[3] = rn_mul(b, rn_sub(rn_add(rn_sub(T(2), ux6), uxx9), uu));
+    e[4] = rn_mul(b, rn_sub(rn_add(rn_sub(T(2), uy6), uyy9), uu));
+    e[5] = rn_mul(c, rn_add(rn_add(rn_add(T(1), p3), uxy9), uu));
+    e[6] = rn_mul(c, rn_add(rn_sub(rn_sub(T(1), m3), uxy9), uu));
+    e[7] = rn_mul(c, rn_add(rn_add(rn_sub(T(1), p3), uxy9), uu));
+    e[8] = rn_mul(c, rn_add(rn_sub(rn_add(T(1), m3), uxy9), uu));
+}
+
+// PoiseuilleFlow.py:49-53: rho = np.sum(grid, axis=0) (f0..f8 in order),
+// ux = ((f1+f5+f8) - (f3+f6+f7))/rho, uy = ((f2+f5+f6) - (f4+f7+f8))/rho.
+template <typename T>
+__device__ __forceinline__ void sf_moments(const T (&f)[9], T &rho, T &ux, T &uy)
+{
+    rho = rn_add(rn_add(rn_add(rn_add(rn_add(rn_add(rn_add(rn_add(f[0], f[1]), f[2]), f[3]), f[4]), f[5]), f[6]), f[7]), f[8]);
+    ux = rn_div(rn_sub(rn_add(rn_add(f[1], f[5]), f[8]), rn_add(rn_add(f[3], f[6]), f[7])), rho);
+    uy = rn_div(rn_sub(rn_add(rn_add(f[2], f[5]), f[6]), rn_add(rn_add(f[4], f[7]), f[8])), rho);
+}
+
+// PoiseuilleFlow.py:45-47: grid -= relaxation * (grid - feq)
+template <typename T>
+__device__ __forceinline__ void sf_collide(T (&f)[9], T omega)
+{
+    T rho, ux, uy, e[9];
+    sf_moments<T>(f, rho, ux, uy);
+    sf_equilibrium<T>(rho, ux, uy, e);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = rn_sub(f[i], rn_mul(omega, rn_sub(f[i], e[i])));
+}
+
 // Moments as the reference's drivers compute them for output
 // (cavity_opt2.py:280-281): rho = np.sum(f, axis=0) accumulates f0..f8 in order.
 template <typename T>

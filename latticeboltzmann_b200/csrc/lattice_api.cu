@@ -44,6 +44,8 @@ struct lb_lattice {
 
 namespace {
 
+int grid_for(long long n, int block);
+
 DevState *dev_state(lb_lattice *L) { return reinterpret_cast<DevState *>(L->base + L->state_off); }
 
 template <typename T>
@@ -64,8 +66,19 @@ StepParams<T> make_params(lb_lattice *L)
     p.rows_per_tile = L->rows_per_tile;
     p.tiles_l = (p.lny + TILE_L - 1) / TILE_L;
     p.tiles_k = (p.lnx + p.rows_per_tile - 1) / p.rows_per_tile;
-    p.n_perimeter = (long long)p.lny + (p.lnx > 1 ? p.lny : 0) + (p.lny > 1 ? 2 : 1) * (long long)(p.lnx > 2 ? p.lnx - 2 : 0);
+    p.all_rim = L->cfg.boundary >= LB_SF_COUETTE ? 1 : 0;
+    if (p.all_rim) {
+        // simple_flows flavour: wall rules also touch the rows/columns next to the wall layers; on these
+        // small (L2-resident, launch-bound) lattices every cell simply takes the general path.
+        p.n_perimeter = (long long)p.lnx * p.lny;
+        p.tiles_l = p.tiles_k = 0;
+    } else {
+        p.n_perimeter = (long long)p.lny + (p.lnx > 1 ? p.lny : 0) + (p.lny > 1 ? 2 : 1) * (long long)(p.lnx > 2 ? p.lnx - 2 : 0);
+    }
     p.n_rim_ctas = (int)((p.n_perimeter + TILE_L - 1) / TILE_L);
+    p.sf_uw6 = (T)((1.0 / 6.0) * L->cfg.u_wall);
+    p.rho_in = (T)L->cfg.rho_in;
+    p.rho_out = (T)L->cfg.rho_out;
     p.omega = (T)L->cfg.omega;
     p.u_wall = (T)L->cfg.u_wall;
     for (int i = 0; i < 9; ++i) {
@@ -109,9 +122,33 @@ int launch_step(lb_lattice *L, bool collide)
     case LB_CAVITY_XPERIODIC:
         return exact ? launch_step_bc<T, BC_CAVITY_XPERIODIC, true>(L, p, collide)
                      : launch_step_bc<T, BC_CAVITY_XPERIODIC, false>(L, p, collide);
+    case LB_SF_COUETTE:
+        return launch_step_bc<T, BC_SF_COUETTE, true>(L, p, collide);
+    case LB_SF_POISEUILLE:
+        return launch_step_bc<T, BC_SF_POISEUILLE, true>(L, p, collide);
+    case LB_SF_SLIDING_LID:
+        return launch_step_bc<T, BC_SF_SLIDING_LID, true>(L, p, collide);
     default:
-        return lbm_fail(LB_ERR_INVALID, "boundary mode %d is not implemented by the fused step", L->cfg.boundary);
+        return lbm_fail(LB_ERR_INVALID, "unknown boundary mode %d", L->cfg.boundary);
     }
+}
+
+// simple_flows step orders.  The pre-kernels rewrite the current buffer in
+// place, so the ghost frame (periodic copies) is refreshed before the pull.
+template <typename T>
+int launch_sf_prologue(lb_lattice *L)
+{
+    const StepParams<T> p = make_params<T>(L);
+    const long long n = (long long)p.lnx * p.lny;
+    if (L->cfg.boundary == LB_SF_COUETTE)
+        sf_collide_inplace_kernel<T><<<grid_for(n, 256), 256, 0, L->stream>>>(p);
+    else if (L->cfg.boundary == LB_SF_POISEUILLE)
+        sf_pressure_kernel<T><<<grid_for(p.lny, 128), 128, 0, L->stream>>>(p);
+    else
+        return 0;
+    halo_refresh_kernel<T><<<grid_for(2ll * (p.lnx + p.lny), 256), 256, 0, L->stream>>>(p);
+    L->launches += 2;
+    return 0;
 }
 
 int check_ready(lb_lattice *L)
@@ -155,6 +192,13 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     // sequential overwrites (cavity_opt2.py:134-177) alias top and bottom and the gather form does not apply.
     if (cfg->boundary != LB_PERIODIC && (cfg->gny < 2 || (cfg->boundary != LB_CAVITY_XPERIODIC && cfg->gnx < 2)))
         return lbm_fail(LB_ERR_INVALID, "wall-bounded lattices need at least 2 cells across each walled direction");
+    if (cfg->boundary >= LB_SF_COUETTE) {
+        // simple_flows flavour (config 2): fp64 like the numpy reference, one block, lattice includes the wall layers
+        if (cfg->dtype != LB_F64) return lbm_fail(LB_ERR_INVALID, "simple_flows boundaries are fp64 only (the reference is numpy float64)");
+        if (cfg->x0 != 0 || cfg->y0 != 0 || cfg->lnx != cfg->gnx || cfg->lny != cfg->gny)
+            return lbm_fail(LB_ERR_INVALID, "simple_flows boundaries run on a single block");
+        if (cfg->gnx < 3 || cfg->gny < 3) return lbm_fail(LB_ERR_INVALID, "simple_flows lattices (wall layers included) need >= 3 cells per direction");
+    }
     if (lb_device_count() <= 0)
         return lbm_fail(LB_ERR_NO_DEVICE, "no CUDA device visible: liblbm_b200 has no CPU fallback");
     LBM_CUDA(cudaSetDevice(cfg->device));
@@ -361,8 +405,12 @@ int lb_step(lb_lattice *L, int64_t nsteps)
     if (int r = check_ready(L)) return r;
     if (nsteps < 0) return lbm_fail(LB_ERR_INVALID, "nsteps < 0");
     LBM_CUDA(cudaSetDevice(L->cfg.device));
+    const bool sf = L->cfg.boundary >= LB_SF_COUETTE;
     for (int64_t s = 0; s < nsteps; ++s) {
-        int r = L->cfg.dtype == LB_F64 ? launch_step<double>(L, true) : launch_step<float>(L, true);
+        if (sf) launch_sf_prologue<double>(L);
+        // Couette collides BEFORE streaming (prologue), so its fused pass streams + reflects only.
+        const bool collide = L->cfg.boundary != LB_SF_COUETTE;
+        int r = L->cfg.dtype == LB_F64 ? launch_step<double>(L, collide) : launch_step<float>(L, collide);
         if (r) return r;
         L->launches++;
         L->steps++;
@@ -431,10 +479,12 @@ int lb_moments(lb_lattice *L, void *rho, void *ux, void *uy)
     const size_t bytes = (size_t)n * L->elem;
     if (!L->d_mom) LBM_CUDA(cudaMalloc(&L->d_mom, 3 * bytes));
     char *d = static_cast<char *>(L->d_mom);
-    if (L->cfg.dtype == LB_F64)
-        moments_kernel<double><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<double>(L), (double *)d, (double *)(d + bytes), (double *)(d + 2 * bytes));
+    if (L->cfg.boundary >= LB_SF_COUETTE)
+        moments_kernel<double, true><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<double>(L), (double *)d, (double *)(d + bytes), (double *)(d + 2 * bytes));
+    else if (L->cfg.dtype == LB_F64)
+        moments_kernel<double, false><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<double>(L), (double *)d, (double *)(d + bytes), (double *)(d + 2 * bytes));
     else
-        moments_kernel<float><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<float>(L), (float *)d, (float *)(d + bytes), (float *)(d + 2 * bytes));
+        moments_kernel<float, false><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<float>(L), (float *)d, (float *)(d + bytes), (float *)(d + 2 * bytes));
     LBM_CUDA(cudaGetLastError());
     L->launches++;
     void *h[3] = {rho, ux, uy};

@@ -28,7 +28,7 @@
 
 namespace lbm {
 
-enum BoundaryKind { BC_PERIODIC = 0, BC_CAVITY = 1, BC_CAVITY_XPERIODIC = 2 };
+enum BoundaryKind { BC_PERIODIC = 0, BC_CAVITY = 1, BC_CAVITY_XPERIODIC = 2, BC_SF_COUETTE = 3, BC_SF_POISEUILLE = 4, BC_SF_SLIDING_LID = 5 };
 
 constexpr unsigned long long HALO_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 
@@ -63,6 +63,7 @@ __device__ __forceinline__ T ld_f(const T *p)
 template <typename T>
 __device__ __forceinline__ void decode_perimeter(const StepParams<T> &p, long long t, int &k, int &l)
 {
+    if (p.all_rim) { k = (int)(t / p.lny); l = (int)(t - (long long)k * p.lny); return; }
     const long long a = p.lny, b = (p.lnx > 1) ? p.lny : 0, c = (p.lnx > 2) ? p.lnx - 2 : 0;
     if (t < a) { k = 0; l = (int)t; }
     else if (t < a + b) { k = p.lnx - 1; l = (int)(t - a); }
@@ -121,7 +122,34 @@ __device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__r
 #pragma unroll
     for (int i = 0; i < 9; ++i) f[i] = ld_f<RIM>(reinterpret_cast<const T *>(sp + p.ld_off[i]));
 
-    if (RIM && BC != BC_PERIODIC) {
+    if (RIM && BC >= BC_SF_COUETTE) {
+        // simple_flows flavour: explicit wall LAYERS at l = 0 / T (and k = 0 / X for
+        // the sliding lid); after the periodic pull, populations that entered a wall layer are copied back
+        // into the adjacent fluid row/column -- written here as a gather from the pre-stream state.
+        // Single block only, so local == global coordinates.
+        const int X = p.lnx - 1, Tt = p.lny - 1;
+#define LBM_PRE(I, DK, DL) ld_f<true>(src + (long long)(I) * S + c + (long long)(DK) * P + (DL))
+        if (BC == BC_SF_SLIDING_LID && l >= 1 && l <= Tt - 1) {     // slidingLid.py:72-78
+            if (k == 1) { f[QE] = LBM_PRE(QW, 0, 0); f[QNE] = LBM_PRE(QSW, 0, 1); f[QSE] = LBM_PRE(QNW, 0, -1); }
+            if (k == X - 1) { f[QW] = LBM_PRE(QE, 0, 0); f[QNW] = LBM_PRE(QSE, 0, 1); f[QSW] = LBM_PRE(QNE, 0, -1); }
+        }
+        if (k >= 1 && k <= X - 1) {                                  // PoiseuilleFlow.py:65-74, slidingLid.py:83-91
+            if (l == 1) { f[QN] = LBM_PRE(QS, 0, 0); f[QNE] = LBM_PRE(QSW, 1, 0); f[QNW] = LBM_PRE(QSE, -1, 0); }
+            if (l == Tt - 1) {
+                const T g2 = LBM_PRE(QN, 0, 0), g5 = LBM_PRE(QNE, -1, 0), g6 = LBM_PRE(QNW, 1, 0);
+                T shift = p.sf_uw6;
+                if (BC == BC_SF_SLIDING_LID) {                      // rho_wall, slidingLid.py:87-91
+                    const T g0 = LBM_PRE(Q0, 0, 1), g1 = LBM_PRE(QE, -1, 1), g3 = LBM_PRE(QW, 1, 1);
+                    const T rw = rn_add(rn_add(rn_add(rn_mul(T(2), rn_add(rn_add(g2, g5), g6)), g0), g1), g3);
+                    shift = rn_mul(p.sf_uw6, rw);
+                }
+                f[QS] = g2;
+                f[QSW] = rn_sub(g5, shift);
+                f[QSE] = rn_add(g6, shift);
+            }
+        }
+#undef LBM_PRE
+    } else if (RIM && BC != BC_PERIODIC) {
         // SURVEY.md App. A.2 == cavity_opt2.py:133-177 as a gather.  Predicates on
         // global coordinates; the wall sits half a cell outside the lattice.
         const long long gk = p.x0 + k, gl = p.y0 + l;
@@ -162,7 +190,12 @@ __device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__r
         }
     }
 
-    if (COLLIDE) d2q9_collide<T, EXACT>(f, p.omega);
+    if (COLLIDE) {
+        if (BC >= BC_SF_COUETTE)
+            sf_collide<T>(f, p.omega);
+        else
+            d2q9_collide<T, EXACT>(f, p.omega);
+    }
 
     // stores walk the populations with one stride (a 9-entry offset table would be hoisted into 18 registers)
     T *dp = dst + c;
@@ -283,7 +316,7 @@ __global__ void init_equilibrium_kernel(const __grid_constant__ StepParams<T> p,
 }
 
 // rho, ux, uy of the current buffer into dense (lnx, lny) arrays (cavity_opt2.py:280-281).
-template <typename T>
+template <typename T, bool SF>
 __global__ void moments_kernel(const __grid_constant__ StepParams<T> p, T *__restrict__ rho, T *__restrict__ ux,
                                T *__restrict__ uy)
 {
@@ -296,10 +329,60 @@ __global__ void moments_kernel(const __grid_constant__ StepParams<T> p, T *__res
 #pragma unroll
         for (int i = 0; i < 9; ++i) f[i] = src[i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L)];
         T r, x, y;
-        d2q9_moments<T>(f, r, x, y);
+        if (SF)
+            sf_moments<T>(f, r, x, y);      // PoiseuilleFlow.py:49-53
+        else
+            d2q9_moments<T>(f, r, x, y);
         if (rho) rho[t] = r;
         if (ux) ux[t] = x;
         if (uy) uy[t] = y;
+    }
+}
+
+// simple_flows: in-place collision of the whole current buffer (Couette's step order is
+// moments -> collide -> stream -> reflect, PoiseuilleFlow.py:107-111).
+template <typename T>
+__global__ void sf_collide_inplace_kernel(const __grid_constant__ StepParams<T> p)
+{
+    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    T *buf = p.buf[par];
+    const long long n = (long long)p.lnx * p.lny;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / p.lny), l = (int)(t % p.lny);
+        T *q = buf + (long long)(k + 1) * p.pitch + (l + PAD_L);
+        T f[9];
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = q[i * p.pop_stride];
+        sf_collide<T>(f, p.omega);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) q[i * p.pop_stride] = f[i];
+    }
+}
+
+// simple_flows: pressure-periodic inlet/outlet (PoiseuilleFlow.py:76-88), in place on rows k = 0 and
+// k = X of the current buffer:  f[:,0,l] = feq(rho_in, u[X-1,l]) + (f[:,X-1,l] - feq[:,X-1,l]),
+//                               f[:,X,l] = feq(rho_out, u[1,l]) + (f[:,1,l]   - feq[:,1,l]).
+template <typename T>
+__global__ void sf_pressure_kernel(const __grid_constant__ StepParams<T> p)
+{
+    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    T *buf = p.buf[par];
+    const int X = p.lnx - 1;
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < p.lny; l += gridDim.x * blockDim.x) {
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+            const int ks = side == 0 ? X - 1 : 1, kd = side == 0 ? 0 : X;
+            const T *q = buf + (long long)(ks + 1) * p.pitch + (l + PAD_L);
+            T f[9], e[9], en[9], rho, ux, uy;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) f[i] = q[i * p.pop_stride];
+            sf_moments<T>(f, rho, ux, uy);
+            sf_equilibrium<T>(rho, ux, uy, e);
+            sf_equilibrium<T>(side == 0 ? p.rho_in : p.rho_out, ux, uy, en);
+            T *d = buf + (long long)(kd + 1) * p.pitch + (l + PAD_L);
+#pragma unroll
+            for (int i = 0; i < 9; ++i) d[i * p.pop_stride] = rn_add(en[i], rn_sub(f[i], e[i]));
+        }
     }
 }
 
