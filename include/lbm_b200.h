@@ -145,6 +145,12 @@ LB_API int lb_step(lb_lattice *lat, int64_t nsteps);
 /* Stream + boundary handling WITHOUT the collision (PyLB.stream /
  * stream_and_bounce_back as stand-alone operations, cavity_opt2.py:109-177).   */
 LB_API int lb_stream_only(lb_lattice *lat, int64_t nsteps);
+/* ONE time step with HOST input and output (the reference's calling convention: the loop body
+ * of cavity_opt2.py:275-277 applied to a host f_ikl): rows are uploaded, updated and downloaded
+ * slab by slab on three streams so that H2D, compute and D2H overlap.  host_out may alias
+ * host_in; both are C-contiguous (9, lnx, lny).  Single self-connected block; returns when
+ * host_out is complete.  Pinned host memory is required for real overlap.              */
+LB_API int lb_step_host(lb_lattice *lat, const void *host_in, void *host_out, int nslabs);
 /* Same, bracketed by CUDA events on the launching stream; returns elapsed ms.  */
 LB_API int lb_step_timed(lb_lattice *lat, int64_t nsteps, float *elapsed_ms);
 LB_API int64_t lb_steps_done(lb_lattice *lat);

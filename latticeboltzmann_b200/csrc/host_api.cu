@@ -170,10 +170,14 @@ int step_host(void *f, int dtype, int64_t nx, int64_t ny, int boundary, double o
     lb_export self;
     r = lb_get_export(L, &self);
     for (int d = 0; !r && d < LB_NUM_DIRS; ++d) r = lb_connect(L, d, &self);
-    if (!r) r = lb_upload_f(L, f);
-    if (!r) r = lb_halo_refresh(L);
-    if (!r) r = lb_step(L, nsteps);
-    if (!r) r = lb_download_f(L, f);
+    if (nsteps == 1) {
+        if (!r) r = lb_step_host(L, f, f, 16);      // H2D / compute / D2H overlapped slab by slab
+    } else {
+        if (!r) r = lb_upload_f(L, f);
+        if (!r) r = lb_halo_refresh(L);
+        if (!r) r = lb_step(L, nsteps);
+        if (!r) r = lb_download_f(L, f);
+    }
     if (!r) r = lb_health(L);
     lb_destroy(L);
     return r;

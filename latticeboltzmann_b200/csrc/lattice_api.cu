@@ -40,6 +40,10 @@ struct lb_lattice {
     int64_t probe_capacity = 0, probe_l_local = -1, probe_step0 = 0;
     // scratch for moments
     void *d_mom = nullptr;
+    // slab-pipelined host step
+    cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
+    std::vector<cudaEvent_t> ev_up, ev_done;
+    cudaEvent_t ev_tail = nullptr, ev_fin = nullptr;
 };
 
 namespace {
@@ -146,7 +150,7 @@ int launch_sf_prologue(lb_lattice *L)
         sf_pressure_kernel<T><<<grid_for(p.lny, 128), 128, 0, L->stream>>>(p);
     else
         return 0;
-    halo_refresh_kernel<T><<<grid_for(2ll * (p.lnx + p.lny), 256), 256, 0, L->stream>>>(p);
+    halo_refresh_kernel<T><<<grid_for(2ll * (p.lnx + p.lny), 256), 256, 0, L->stream>>>(p, 0, p.lnx);
     L->launches += 2;
     return 0;
 }
@@ -240,6 +244,12 @@ int lb_destroy(lb_lattice *L)
     if (L->d_uyk) cudaFree(L->d_uyk);
     if (L->d_series) cudaFree(L->d_series);
     if (L->d_mom) cudaFree(L->d_mom);
+    for (auto e : L->ev_up) cudaEventDestroy(e);
+    for (auto e : L->ev_done) cudaEventDestroy(e);
+    if (L->ev_tail) cudaEventDestroy(L->ev_tail);
+    if (L->ev_fin) cudaEventDestroy(L->ev_fin);
+    if (L->s_h2d) cudaStreamDestroy(L->s_h2d);
+    if (L->s_d2h) cudaStreamDestroy(L->s_d2h);
     if (L->ev0) cudaEventDestroy(L->ev0);
     if (L->ev1) cudaEventDestroy(L->ev1);
     if (L->own_stream) cudaStreamDestroy(L->own_stream);
@@ -345,9 +355,9 @@ int lb_halo_refresh(lb_lattice *L)
     LBM_CUDA(cudaSetDevice(L->cfg.device));
     const long long n_rim = 2 * (L->cfg.lnx + L->cfg.lny);
     if (L->cfg.dtype == LB_F64)
-        halo_refresh_kernel<double><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(make_params<double>(L));
+        halo_refresh_kernel<double><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(make_params<double>(L), 0, (int)L->cfg.lnx);
     else
-        halo_refresh_kernel<float><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(make_params<float>(L));
+        halo_refresh_kernel<float><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(make_params<float>(L), 0, (int)L->cfg.lnx);
     LBM_CUDA(cudaGetLastError());
     L->launches++;
     return 0;
@@ -442,6 +452,124 @@ int lb_stream_only(lb_lattice *L, int64_t nsteps)
     }
     LBM_CUDA(cudaGetLastError());
     return 0;
+}
+
+}  // extern "C"
+
+namespace {
+
+template <typename T>
+int launch_rows(lb_lattice *L, const StepParams<T> &p, int k_lo, int k_hi)
+{
+    const int tiles_l = (p.lny + TILE_L - 1) / TILE_L;
+    const int grid = (k_hi - k_lo) * tiles_l;
+    const bool exact = L->cfg.arith == LB_ARITH_EXACT;
+#define LBM_ROWS(BC)                                                                                \
+    (exact ? step_rows_kernel<T, BC, true><<<grid, TILE_L, 0, L->stream>>>(p, k_lo, k_hi)            \
+           : step_rows_kernel<T, BC, false><<<grid, TILE_L, 0, L->stream>>>(p, k_lo, k_hi))
+    switch (L->cfg.boundary) {
+    case LB_PERIODIC: LBM_ROWS(BC_PERIODIC); break;
+    case LB_CAVITY: LBM_ROWS(BC_CAVITY); break;
+    case LB_CAVITY_XPERIODIC: LBM_ROWS(BC_CAVITY_XPERIODIC); break;
+    default: return lbm_fail(LB_ERR_INVALID, "lb_step_host supports the periodic and cavity boundaries");
+    }
+#undef LBM_ROWS
+    return 0;
+}
+
+// rows [k_lo, k_hi) of all 9 populations between the host array (9, lnx, lny) and buffer `par`
+int copy_rows(lb_lattice *L, void *host, int par, int64_t k_lo, int64_t k_hi, bool upload, cudaStream_t st)
+{
+    const size_t e = L->elem, row = (size_t)L->cfg.lny * e;
+    char *buf = L->base + (size_t)par * L->buf_bytes;
+    for (int i = 0; i < 9; ++i) {
+        char *d = buf + ((size_t)i * L->pop_stride + (size_t)(k_lo + 1) * L->pitch + PAD_L) * e;
+        char *h = static_cast<char *>(host) + ((size_t)i * L->cfg.lnx + (size_t)k_lo) * row;
+        if (upload)
+            LBM_CUDA(cudaMemcpy2DAsync(d, (size_t)L->pitch * e, h, row, row, (size_t)(k_hi - k_lo), cudaMemcpyHostToDevice, st));
+        else
+            LBM_CUDA(cudaMemcpy2DAsync(h, row, d, (size_t)L->pitch * e, row, (size_t)(k_hi - k_lo), cudaMemcpyDeviceToHost, st));
+    }
+    return 0;
+}
+
+template <typename T>
+int step_host_pipelined(lb_lattice *L, const void *host_in, void *host_out, int nslabs)
+{
+    const int64_t lnx = L->cfg.lnx;
+    if (nslabs < 1) nslabs = 1;
+    if (nslabs > lnx) nslabs = (int)lnx;
+    if (!L->s_h2d) {
+        LBM_CUDA(cudaStreamCreateWithFlags(&L->s_h2d, cudaStreamNonBlocking));
+        LBM_CUDA(cudaStreamCreateWithFlags(&L->s_d2h, cudaStreamNonBlocking));
+        LBM_CUDA(cudaEventCreateWithFlags(&L->ev_tail, cudaEventDisableTiming));
+        LBM_CUDA(cudaEventCreateWithFlags(&L->ev_fin, cudaEventDisableTiming));
+    }
+    while ((int)L->ev_up.size() < nslabs) {
+        cudaEvent_t a, b;
+        LBM_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        LBM_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        L->ev_up.push_back(a);
+        L->ev_done.push_back(b);
+    }
+    const StepParams<T> p = make_params<T>(L);
+    const int par = (int)(L->steps & 1);
+    void *hin = const_cast<void *>(host_in);
+    auto lo = [&](int j) { return lnx * j / nslabs; };
+    // everything already queued on the lattice's stream (previous steps) must precede the uploads
+    LBM_CUDA(cudaEventRecord(L->ev_fin, L->stream));
+    LBM_CUDA(cudaStreamWaitEvent(L->s_h2d, L->ev_fin, 0));
+    LBM_CUDA(cudaStreamWaitEvent(L->s_d2h, L->ev_fin, 0));
+    // the last row first: slab 0 pulls its periodic image (ghost row -1)
+    if (int r = copy_rows(L, hin, par, lnx - 1, lnx, true, L->s_h2d)) return r;
+    LBM_CUDA(cudaEventRecord(L->ev_tail, L->s_h2d));
+    for (int j = 0; j < nslabs; ++j) {
+        if (int r = copy_rows(L, hin, par, lo(j), lo(j + 1), true, L->s_h2d)) return r;
+        LBM_CUDA(cudaEventRecord(L->ev_up[j], L->s_h2d));
+    }
+    const long long n_rim = 2 * (L->cfg.lnx + L->cfg.lny);
+    LBM_CUDA(cudaStreamWaitEvent(L->stream, L->ev_tail, 0));
+    halo_refresh_kernel<T><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(p, (int)lnx - 1, (int)lnx);
+    LBM_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[0], 0));
+    halo_refresh_kernel<T><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(p, (int)lo(0), (int)lo(1));
+    for (int j = 0; j < nslabs; ++j) {
+        if (j + 1 < nslabs) {   // slab j pulls from the first row of slab j+1 (and its ghost columns)
+            LBM_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[j + 1], 0));
+            halo_refresh_kernel<T><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(p, (int)lo(j + 1), (int)lo(j + 2));
+        }
+        if (int r = launch_rows<T>(L, p, (int)lo(j), (int)lo(j + 1))) return r;
+        LBM_CUDA(cudaEventRecord(L->ev_done[j], L->stream));
+        LBM_CUDA(cudaStreamWaitEvent(L->s_d2h, L->ev_done[j], 0));
+        if (int r = copy_rows(L, host_out, par ^ 1, lo(j), lo(j + 1), false, L->s_d2h)) return r;
+        L->launches += 2;
+    }
+    advance_step_kernel<<<1, 1, 0, L->stream>>>(dev_state(L));
+    L->launches += 2;
+    L->steps++;
+    LBM_CUDA(cudaGetLastError());
+    LBM_CUDA(cudaEventRecord(L->ev_fin, L->s_d2h));
+    LBM_CUDA(cudaStreamWaitEvent(L->stream, L->ev_fin, 0));
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    return 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+/* One time step with HOST input and output (the reference's stateless calling convention:
+ * cavity_opt2.py:275-277 on a host f_ikl): rows are uploaded, updated and downloaded slab by slab
+ * on three streams, so H2D, compute and D2H overlap (PCIe full duplex).  host_out may alias host_in.
+ * Single block with its ring closed on itself; pinned host memory is needed for real overlap. */
+int lb_step_host(lb_lattice *L, const void *host_in, void *host_out, int nslabs)
+{
+    if (int r = check_ready(L)) return r;
+    if (!host_in || !host_out) return lbm_fail(LB_ERR_INVALID, "null host buffer");
+    for (int d = 0; d < LB_NUM_DIRS; ++d)
+        if (L->nbr[d].base != L->base) return lbm_fail(LB_ERR_STATE, "lb_step_host needs a single self-connected block");
+    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    return L->cfg.dtype == LB_F64 ? step_host_pipelined<double>(L, host_in, host_out, nslabs)
+                                  : step_host_pipelined<float>(L, host_in, host_out, nslabs);
 }
 
 int lb_step_timed(lb_lattice *L, int64_t nsteps, float *ms)

@@ -278,9 +278,33 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
     }
 }
 
+// Rows [k_lo, k_hi) of one step through the general (rim) cell path, without the flag protocol and
+// without touching the step counter: the building block of the slab-pipelined host step
+// (lb_step_host), where the host orders H2D -> compute -> D2H per slab with events.
+template <typename T, int BC, bool EXACT>
+__global__ void __launch_bounds__(TILE_L) step_rows_kernel(const __grid_constant__ StepParams<T> p, int k_lo, int k_hi)
+{
+    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    const T *__restrict__ src = p.buf[par];
+    T *__restrict__ dst = p.buf[par ^ 1];
+    const int tiles_l = (p.lny + TILE_L - 1) / TILE_L;
+    const int k = k_lo + (int)blockIdx.x / tiles_l;
+    const int l = ((int)blockIdx.x % tiles_l) * TILE_L + threadIdx.x;
+    if (k < k_hi && l < p.lny) update_cell<T, BC, EXACT, true, true>(p, src, dst, par ^ 1, k, l);
+}
+
+// Completes a host-ordered step of a self-connected block: bump the step counter and post the
+// block's own halo flags so that a following fused (flag-ordered) step finds them satisfied.
+__global__ void advance_step_kernel(DevState *st)
+{
+    const unsigned long long s = st->step + 1ull;
+    st->step = s;
+    for (int d = 0; d < NUM_DIRS; ++d) st->flag_in[d] = s;
+}
+
 // Push the rim of the CURRENT buffer (used once after init / upload).
 template <typename T>
-__global__ void halo_refresh_kernel(const __grid_constant__ StepParams<T> p)
+__global__ void halo_refresh_kernel(const __grid_constant__ StepParams<T> p, int k_lo, int k_hi)
 {
     const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
     const T *src = p.buf[par];
@@ -291,6 +315,7 @@ __global__ void halo_refresh_kernel(const __grid_constant__ StepParams<T> p)
         else if (t < 2ll * p.lny) { k = p.lnx - 1; l = (int)(t - p.lny); }
         else if (t < 2ll * p.lny + p.lnx) { k = (int)(t - 2ll * p.lny); l = 0; }
         else { k = (int)(t - 2ll * p.lny - p.lnx); l = p.lny - 1; }
+        if (k < k_lo || k >= k_hi) continue;      // row-range variant used by the pipelined host step
         T f[9];
 #pragma unroll
         for (int i = 0; i < 9; ++i) f[i] = __ldcg(src + i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L));

@@ -104,6 +104,16 @@ class Block:
         check(self.lib.lb_step_timed(self.h, n, ctypes.byref(ms)))
         return ms.value
 
+    def step_host(self, f_in, f_out=None, nslabs=16):
+        """One step with HOST input/output (the reference's stateless convention), H2D / compute / D2H
+        overlapped slab by slab.  f_out defaults to f_in (in place).  Arrays: C-contiguous (9, lnx, lny)."""
+        f_out = f_in if f_out is None else f_out
+        for a in (f_in, f_out):
+            if not (isinstance(a, np.ndarray) and a.flags.c_contiguous and a.dtype == self.dtype
+                    and a.shape == (9, self.lnx, self.lny)):
+                raise TypeError("step_host needs C-contiguous %s arrays of shape (9, %d, %d)" % (self.dtype, self.lnx, self.lny))
+        check(self.lib.lb_step_host(self.h, np_ptr(f_in), np_ptr(f_out), int(nslabs)))
+
     def sync(self):
         check(self.lib.lb_sync(self.h))
 
