@@ -46,6 +46,8 @@ def workload(name, n_gpus):
     if n_gpus not in grid:
         raise SystemExit("--gpus must be 1, 2, 4 or 8")
     ndx, ndy = grid[n_gpus]
+    if os.environ.get("LBM_BENCH_GRID"):          # developer override, e.g. "1x2"
+        ndx, ndy = (int(v) for v in os.environ["LBM_BENCH_GRID"].split("x"))
     if name == "weak16384":
         n = 16384
         return n * ndx, n * ndy, ndx, ndy, "weak", "lid-driven cavity, %dx%d cells per GPU, Re=1000, %dx%d blocks" % (n, n, ndx, ndy)
@@ -259,7 +261,14 @@ def main():
     traffic = ncu_traffic_per_launch()
 
     e2e = None
-    if not args.no_e2e:
+    need = 9 * b.lnx * b.lny * 8 * world
+    try:
+        avail = [int(x.split()[1]) * 1024 for x in open("/proc/meminfo") if x.startswith("MemAvailable")][0]
+    except Exception:
+        avail = 0
+    if not args.no_e2e and need * 1.5 > avail:
+        e2e = {"value": None, "unit": "MLUPS", "skipped": "pinned host staging of %.0f GB exceeds 2/3 of available host memory (%.0f GB)" % (need / 1e9, avail / 1e9)}
+    elif not args.no_e2e:
         try:
             sec, nbytes = e2e_host_step(lat, args.e2e_steps)
             sec = D.max_over_ranks(sec)

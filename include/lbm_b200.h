@@ -101,6 +101,8 @@ typedef struct lb_export {
     int64_t pitch;               /* row pitch in elements                               */
     int64_t pop_stride;          /* population stride in elements                       */
     int64_t buf_bytes;           /* bytes of one f buffer (there are two, A then B)     */
+    int64_t ycol_offset;         /* byte offset of the ghost-column arrays (A then B)   */
+    int64_t ycol_bytes;          /* bytes of one ghost-column array                     */
     int64_t state_offset;        /* byte offset of the device state block (flags)       */
     int64_t total_bytes;
 } lb_export;

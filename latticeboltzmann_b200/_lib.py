@@ -33,7 +33,8 @@ class LbConfig(ctypes.Structure):
 class LbExport(ctypes.Structure):
     _fields_ = [("ipc_mem_handle", ctypes.c_uint8 * 64), ("local_base", ctypes.c_uint64), ("pid", c_i64),
                 ("device", ctypes.c_int32), ("dtype", ctypes.c_int32), ("lnx", c_i64), ("lny", c_i64),
-                ("pitch", c_i64), ("pop_stride", c_i64), ("buf_bytes", c_i64), ("state_offset", c_i64),
+                ("pitch", c_i64), ("pop_stride", c_i64), ("buf_bytes", c_i64), ("ycol_offset", c_i64),
+                ("ycol_bytes", c_i64), ("state_offset", c_i64),
                 ("total_bytes", c_i64)]
 
 
@@ -95,7 +96,7 @@ def load(build_if_missing=True):
     global _lib
     if _lib is not None:
         return _lib
-    path = _build.SO
+    path = os.environ.get("LBM_NATIVE_LIB") or _build.SO      # developer override (A/B kernel experiments)
     if not os.path.exists(path):
         if not build_if_missing:
             raise LbmError("native library %s is missing (run `python -m latticeboltzmann_b200.build`)" % path)

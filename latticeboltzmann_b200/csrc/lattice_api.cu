@@ -26,7 +26,7 @@ struct lb_lattice {
     lb_config cfg{};
     size_t elem = 8;
     char *base = nullptr;
-    size_t buf_bytes = 0, state_off = 0, total_bytes = 0;
+    size_t buf_bytes = 0, ycol_off = 0, ycol_bytes = 0, state_off = 0, total_bytes = 0;
     long long pitch = 0, pop_stride = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -58,6 +58,8 @@ StepParams<T> make_params(lb_lattice *L)
     StepParams<T> p{};
     p.buf[0] = reinterpret_cast<T *>(L->base);
     p.buf[1] = reinterpret_cast<T *>(L->base + L->buf_bytes);
+    p.ycol[0] = reinterpret_cast<T *>(L->base + L->ycol_off);
+    p.ycol[1] = reinterpret_cast<T *>(L->base + L->ycol_off + L->ycol_bytes);
     p.st = dev_state(L);
     p.pop_stride = L->pop_stride;
     p.pitch = L->pitch;
@@ -93,6 +95,8 @@ StepParams<T> make_params(lb_lattice *L)
         if (!n.connected) continue;
         p.nbr[d].buf[0] = reinterpret_cast<T *>(n.base);
         p.nbr[d].buf[1] = reinterpret_cast<T *>(n.base + n.exp.buf_bytes);
+        p.nbr[d].ycol[0] = reinterpret_cast<T *>(n.base + n.exp.ycol_offset);
+        p.nbr[d].ycol[1] = reinterpret_cast<T *>(n.base + n.exp.ycol_offset + n.exp.ycol_bytes);
         p.nbr[d].flag_in = reinterpret_cast<DevState *>(n.base + n.exp.state_offset)->flag_in;
         p.nbr[d].pop_stride = n.exp.pop_stride;
         p.nbr[d].pitch = n.exp.pitch;
@@ -215,7 +219,9 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     L->pop_stride = (cfg->lnx + 2) * L->pitch;
     L->buf_bytes = (size_t)9 * L->pop_stride * L->elem;
     L->buf_bytes = (L->buf_bytes + 255) / 256 * 256;
-    L->state_off = 2 * L->buf_bytes;
+    L->ycol_off = 2 * L->buf_bytes;
+    L->ycol_bytes = ((size_t)6 * (cfg->lnx + 2) * L->elem + 255) / 256 * 256;   // one ghost-column array per buffer
+    L->state_off = L->ycol_off + 2 * L->ycol_bytes;
     L->total_bytes = L->state_off + 256;
     cudaError_t e = cudaMalloc(&L->base, L->total_bytes);
     if (e != cudaSuccess) {
@@ -303,6 +309,8 @@ int lb_get_export(lb_lattice *L, lb_export *out)
     out->pitch = L->pitch;
     out->pop_stride = L->pop_stride;
     out->buf_bytes = (int64_t)L->buf_bytes;
+    out->ycol_offset = (int64_t)L->ycol_off;
+    out->ycol_bytes = (int64_t)L->ycol_bytes;
     out->state_offset = (int64_t)L->state_off;
     out->total_bytes = (int64_t)L->total_bytes;
     return 0;

@@ -93,20 +93,26 @@ __device__ __forceinline__ void push_halo(const StepParams<T> &p, int par, int k
         LBM_PUSH(0, p.nbr[0].lnx, l, QNW);
         LBM_PUSH(0, p.nbr[0].lnx, l, QSW);
     }
-    if (yh) {   // +y face -> ghost column -1 of the upper neighbour: N, NE, NW
-        LBM_PUSH(3, k, -1, QN);
-        LBM_PUSH(3, k, -1, QNE);
-        LBM_PUSH(3, k, -1, QNW);
+#define LBM_PUSH_Y(D, SIDE, KK, I)                                                          \
+    do {                                                                                    \
+        const NbrView<T> &nb = p.nbr[D];                                                    \
+        nb.ycol[par][((SIDE) * 3 + ycol_slot(I)) * (long long)(nb.lnx + 2) + ((KK) + 1)] = f[I]; \
+    } while (0)
+    if (yh) {   // +y face -> ghost column -1 (ycol side 0) of the upper neighbour: N, NE, NW
+        LBM_PUSH_Y(3, 0, k, QN);
+        LBM_PUSH_Y(3, 0, k, QNE);
+        LBM_PUSH_Y(3, 0, k, QNW);
     }
-    if (yl) {   // -y face -> ghost column lny of the lower neighbour: S, SW, SE
-        LBM_PUSH(2, k, p.nbr[2].lny, QS);
-        LBM_PUSH(2, k, p.nbr[2].lny, QSW);
-        LBM_PUSH(2, k, p.nbr[2].lny, QSE);
+    if (yl) {   // -y face -> ghost column lny (ycol side 1) of the lower neighbour: S, SW, SE
+        LBM_PUSH_Y(2, 1, k, QS);
+        LBM_PUSH_Y(2, 1, k, QSW);
+        LBM_PUSH_Y(2, 1, k, QSE);
     }
-    if (xh && yh) LBM_PUSH(7, -1, -1, QNE);
-    if (xh && yl) LBM_PUSH(6, -1, p.nbr[6].lny, QSE);
-    if (xl && yh) LBM_PUSH(5, p.nbr[5].lnx, -1, QNW);
-    if (xl && yl) LBM_PUSH(4, p.nbr[4].lnx, p.nbr[4].lny, QSW);
+    if (xh && yh) LBM_PUSH_Y(7, 0, -1, QNE);
+    if (xh && yl) LBM_PUSH_Y(6, 1, -1, QSE);
+    if (xl && yh) LBM_PUSH_Y(5, 0, p.nbr[5].lnx, QNW);
+    if (xl && yl) LBM_PUSH_Y(4, 1, p.nbr[4].lnx, QSW);
+#undef LBM_PUSH_Y
 #undef LBM_PUSH
 }
 
@@ -120,7 +126,14 @@ __device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__r
     const char *sp = reinterpret_cast<const char *>(src + c);
     T f[9];
 #pragma unroll
-    for (int i = 0; i < 9; ++i) f[i] = ld_f<RIM>(reinterpret_cast<const T *>(sp + p.ld_off[i]));
+    for (int i = 0; i < 9; ++i) {
+        if (RIM && cy_of(i) == 1 && l == 0)                  // source (k-cx, -1): ghost column below
+            f[i] = __ldcg(p.ycol[par_dst ^ 1] + (0 * 3 + ycol_slot(i)) * (long long)(p.lnx + 2) + (k - cx_of(i) + 1));
+        else if (RIM && cy_of(i) == -1 && l == p.lny - 1)    // source (k-cx, lny): ghost column above
+            f[i] = __ldcg(p.ycol[par_dst ^ 1] + (1 * 3 + ycol_slot(i)) * (long long)(p.lnx + 2) + (k - cx_of(i) + 1));
+        else
+            f[i] = ld_f<RIM>(reinterpret_cast<const T *>(sp + p.ld_off[i]));
+    }
 
     if (RIM && BC >= BC_SF_COUETTE) {
         // simple_flows flavour: explicit wall LAYERS at l = 0 / T (and k = 0 / X for
