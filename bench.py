@@ -120,14 +120,18 @@ def measured_hbm_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic_per_launch():
-    """dram bytes read+written per step-kernel launch from the committed ncu --set full capture, or None."""
+def ncu_traffic_per_launch(arith, cells):
+    """dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch from the committed ncu
+    captures (profiles/r01_step_kernel_dram.json: one entry per arith x cells-per-launch), or None."""
     p = os.path.join(ROOT, "profiles", "r01_step_kernel_dram.json")
     try:
         with open(p) as fh:
-            return json.load(fh)
+            for e in json.load(fh)["captures"]:
+                if e["arith"] == arith and e["cells_per_launch"] == cells:
+                    return e
     except Exception:
-        return None
+        pass
+    return None
 
 
 def cpu_reference(nx_total, ny_total, omega, steps, warmup, cores=None):
@@ -166,7 +170,7 @@ def run_reference_arm(args):
             "config": {"workload": desc, "nx": nx, "ny": ny, "omega": omega},
             "cpu_baseline": {"value": mlups, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": mlups, "unit": "MLUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def e2e_host_step(lat, steps):
@@ -205,14 +209,35 @@ def e2e_host_step(lat, steps):
     return dt / steps, host.numel() * 8
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Native libraries (NCCL's version banner, ...) print to fd 1; the contract is ONE JSON line on
+    stdout.  Route fd 1 to stderr for the duration of the run and keep the real stdout for the result."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="weak16384", choices=["weak16384", "cavity4096", "strong32768"])
-    ap.add_argument("--arith", default="fast", choices=["fast", "exact"])
+    ap.add_argument("--arith", default="exact", choices=["fast", "exact"],
+                    help="exact: bit-identical to the reference's no-FMA build (default); fast: FMA contraction, <1e-12")
     ap.add_argument("--rows-per-tile", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -258,7 +283,7 @@ def main():
     per_launch_ms = ms / args.steps
     achieved = b.lnx * b.lny * BYTES_PER_CELL / (per_launch_ms * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
-    traffic = ncu_traffic_per_launch()
+    traffic = ncu_traffic_per_launch(args.arith, b.lnx * b.lny)
 
     e2e = None
     need = 9 * b.lnx * b.lny * 8 * world
@@ -297,7 +322,7 @@ def main():
                              "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": b.lnx * b.lny,
                              "traffic_note": (traffic or {}).get("note")},
                 "cpu_baseline": cpu}
-        print(json.dumps(line), flush=True)
+        emit(line)
     import torch.distributed as dist
     if dist.is_initialized():
         dist.barrier()

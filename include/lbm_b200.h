@@ -168,7 +168,7 @@ LB_API int lb_moments(lb_lattice *lat, void *rho, void *ux, void *uy);
 LB_API int lb_probe_shear_enable(lb_lattice *lat, int64_t l_probe_global, const void *uy_k, int64_t capacity);
 LB_API int lb_probe_shear_read(lb_lattice *lat, void *out, int64_t n);
 
-/* Tuning: rows of the lattice handled by one CTA (default 8).                  */
+/* Tuning: rows of the lattice handled by one CTA (default 4).                  */
 LB_API int lb_set_rows_per_tile(lb_lattice *lat, int rows);
 /* Geometry queries (elements). */
 LB_API int64_t lb_pitch(lb_lattice *lat);
@@ -193,6 +193,11 @@ LB_API int lbk_stream_f64(double *f, int64_t nx, int64_t ny);
  * f[9,nx,ny] in place.  boundary is LB_PERIODIC, LB_CAVITY or LB_CAVITY_XPERIODIC. */
 LB_API int lbk_step_host_f32(float *f, int64_t nx, int64_t ny, int boundary, float omega, float u0, int64_t nsteps);
 LB_API int lbk_step_host_f64(double *f, int64_t nx, int64_t ny, int boundary, double omega, double u0, int64_t nsteps);
+
+/* Self-test hook: evaluates the kernel's 3-operation correctly-rounded x/9 and x/6 on the given
+ * bit patterns and counts results that differ from the IEEE division (must be 0).          */
+LB_API int lbk_selftest_div_const_f64(const uint64_t *bits, int64_t n, int64_t *mismatches);
+LB_API int lbk_selftest_div_const_f32(const uint32_t *bits, int64_t n, int64_t *mismatches);
 
 #ifdef __cplusplus
 }

@@ -80,6 +80,8 @@ SYMBOLS = {
     "lbk_collide_f64": (ctypes.c_int, [c_vp, c_i64, ctypes.c_double]),
     "lbk_stream_f32": (ctypes.c_int, [c_vp, c_i64, c_i64]),
     "lbk_stream_f64": (ctypes.c_int, [c_vp, c_i64, c_i64]),
+    "lbk_selftest_div_const_f64": (ctypes.c_int, [c_vp, c_i64, _P(c_i64)]),
+    "lbk_selftest_div_const_f32": (ctypes.c_int, [c_vp, c_i64, _P(c_i64)]),
     "lbk_step_host_f32": (ctypes.c_int, [c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_float, ctypes.c_float, c_i64]),
     "lbk_step_host_f64": (ctypes.c_int, [c_vp, c_i64, c_i64, ctypes.c_int, ctypes.c_double, ctypes.c_double, c_i64]),
 }

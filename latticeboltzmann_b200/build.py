@@ -30,17 +30,19 @@ def _stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build_native(force=False, verbose=False):
-    """Returns the path of the shared library, building it if sources are newer."""
-    if not force and not _stale():
+def build_native(force=False, verbose=False, defines=(), out=None):
+    """Returns the path of the shared library, building it if sources are newer.
+    `defines` / `out` build an experimental variant next to the product library."""
+    if out is None and not force and not _stale():
         return SO
-    objdir = os.path.join(CSRC, "build")
+    so = out or SO
+    objdir = os.path.join(CSRC, "build" if out is None else "build_" + os.path.basename(out))
     os.makedirs(objdir, exist_ok=True)
     objs = []
     procs = []
     for src in SOURCES:
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
-        cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [_nvcc()] + NVCC_FLAGS + ["-D" + d for d in defines] + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)))
         objs.append(obj)
     for src, p in procs:
@@ -49,12 +51,12 @@ def build_native(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [_nvcc(), "-shared", "-o", SO] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    cmd = [_nvcc(), "-shared", "-o", so] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
     r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if r.returncode:
         sys.stderr.write(r.stdout)
         raise RuntimeError("link failed")
-    return SO
+    return so
 
 
 if __name__ == "__main__":

@@ -52,12 +52,47 @@ __device__ __forceinline__ float rn_div(float a, float b)
     return __fdiv_rn(a, b);
 }
 
+// Correctly rounded x / C for the small integer constants C = 9 and C = 6 in three operations:
+//     y = RN(1/C);  q = RN(x*y);  r = x - C*q (exact, one FMA);  q' = RN(q + r*y).
+// Proof sketch (p-bit binary floating point, no over/underflow -- hence the range guard):
+// |q - x/C| < 2 ulp(q), so r = x - C*q is a multiple of ulp(q) smaller than 2C ulp(q) and is
+// exactly representable; the FMA therefore rounds x/C + (r/C)*d with |d| <= 2^-p, a perturbation
+// below 2^-(p-1) ulp(q).  x/C = q + (m/C) ulp(q) with m an integer, and since x itself is
+// representable (a multiple of 4 or 8 ulp(q)) the quotient can neither be a rounding tie nor come
+// closer than ulp(q)/(2C) to one, so the perturbation cannot change the rounding: q' = RN(x/C).
+// (checked against __ddiv_rn / __fdiv_rn on 2^28 random and edge inputs in
+// tests/test_gpu_parity.py::test_exact_constant_division.)
+template <int C>
+__device__ __forceinline__ double rn_div_const(double x)
+{
+    const double y = 1.0 / C;
+    const double ax = fabs(x);
+    if (ax >= 0x1p-900 && ax <= 0x1p900) {
+        const double q = __dmul_rn(x, y);
+        const double r = __fma_rn(-double(C), q, x);
+        return __fma_rn(r, y, q);
+    }
+    return rn_div(x, double(C));
+}
+template <int C>
+__device__ __forceinline__ float rn_div_const(float x)
+{
+    const float y = 1.0f / C;
+    const float ax = fabsf(x);
+    if (ax >= 0x1p-100f && ax <= 0x1p100f) {
+        const float q = __fmul_rn(x, y);
+        const float r = __fmaf_rn(-float(C), q, x);
+        return __fmaf_rn(r, y, q);
+    }
+    return rn_div(x, float(C));
+}
+
 // c/d2q9.h:59-81
 template <typename T, bool EXACT>
 __device__ __forceinline__ void d2q9_equilibrium(T rho, T ux, T uy, T (&e)[9])
 {
     if (EXACT) {
-        const T w1 = rn_div(rho, T(9));            // rho/9
+        const T w1 = rn_div_const<9>(rho);         // rho/9, correctly rounded
         const T w0 = rn_mul(T(4), w1);             // == (4*rho)/9 exactly
         const T w5 = rn_mul(T(0.25), w1);          // == rho/36 exactly
         ux = rn_mul(ux, T(3));
@@ -66,7 +101,7 @@ __device__ __forceinline__ void d2q9_equilibrium(T rho, T ux, T uy, T (&e)[9])
         const T cu6 = rn_add(-ux, uy);
         const T cu7 = rn_sub(-ux, uy);
         const T cu8 = rn_sub(ux, uy);
-        const T uu = rn_div(rn_add(rn_mul(ux, ux), rn_mul(uy, uy)), T(6));
+        const T uu = rn_div_const<6>(rn_add(rn_mul(ux, ux), rn_mul(uy, uy)));
         const T hx = rn_mul(rn_mul(ux, ux), T(0.5));
         const T hy = rn_mul(rn_mul(uy, uy), T(0.5));
         e[0] = rn_mul(w0, rn_sub(T(1), uu));
@@ -140,7 +175,7 @@ __device__ __forceinline__ void sf_equilibrium(T rho, T ux, T uy, T (&e)[9])
     const T uxx9 = rn_mul(rn_mul(T(9), ux), ux);
     const T uyy9 = rn_mul(rn_mul(T(9), uy), uy);
     const T uxy9 = rn_mul(rn_mul(T(9), ux), uy);
-    const T r9 = rn_div(rho, T(9));
+    const T r9 = rn_div_const<9>(rho);
     const T a = rn_mul(T(2), r9), b = rn_mul(T(0.5), r9), c = rn_mul(T(0.25), r9);
     e[0] = rn_mul(a, rn_sub(T(2), uu));
     e[1] = rn_mul(b, rn_sub(rn_add(rn_add(T(2), ux6), uxx9), uu));

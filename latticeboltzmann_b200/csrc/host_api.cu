@@ -58,6 +58,24 @@ __global__ void k_stream(const T *__restrict__ in, T *__restrict__ out, long lon
     }
 }
 
+// Self-check of rn_div_const against the IEEE division intrinsic: counts mismatching bit patterns.
+template <typename T, typename U>
+__global__ void k_check_div_const(const U *bits, long long n, unsigned long long *bad)
+{
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        T x;
+        U b = bits[t];
+        memcpy(&x, &b, sizeof(T));
+        T a9 = rn_div_const<9>(x), a6 = rn_div_const<6>(x);
+        T r9 = sizeof(T) == 8 ? (T)__ddiv_rn((double)x, 9.0) : (T)__fdiv_rn((float)x, 9.0f);
+        T r6 = sizeof(T) == 8 ? (T)__ddiv_rn((double)x, 6.0) : (T)__fdiv_rn((float)x, 6.0f);
+        U ua9, ua6, ur9, ur6;
+        memcpy(&ua9, &a9, sizeof(T)); memcpy(&ua6, &a6, sizeof(T)); memcpy(&ur9, &r9, sizeof(T)); memcpy(&ur6, &r6, sizeof(T));
+        const bool nan9 = (a9 != a9) && (r9 != r9), nan6 = (a6 != a6) && (r6 != r6);
+        if ((ua9 != ur9 && !nan9) || (ua6 != ur6 && !nan6)) atomicAdd(bad, 1ull);
+    }
+}
+
 int grid_for(long long n) { long long g = (n + 255) / 256; return (int)(g < 1 ? 1 : (g > 148 * 32 ? 148 * 32 : g)); }
 
 int need_device()
@@ -185,7 +203,28 @@ int step_host(void *f, int dtype, int64_t nx, int64_t ny, int boundary, double o
 
 }  // namespace
 
+template <typename T, typename U>
+int check_div_const(const U *bits, int64_t n, int64_t *mismatches)
+{
+    if (!bits || !mismatches || n < 0) return lbm_fail(LB_ERR_INVALID, "bad argument");
+    if (int r = need_device()) return r;
+    DevBuf d, b;
+    LBM_CUDA(cudaMalloc(&d.p, (size_t)n * sizeof(U) + 8));
+    LBM_CUDA(cudaMalloc(&b.p, 8));
+    LBM_CUDA(cudaMemset(b.p, 0, 8));
+    LBM_CUDA(cudaMemcpy(d.p, bits, (size_t)n * sizeof(U), cudaMemcpyHostToDevice));
+    k_check_div_const<T, U><<<grid_for(n), 256>>>(static_cast<const U *>(d.p), n, static_cast<unsigned long long *>(b.p));
+    LBM_CUDA(cudaGetLastError());
+    unsigned long long h = 0;
+    LBM_CUDA(cudaMemcpy(&h, b.p, 8, cudaMemcpyDeviceToHost));
+    *mismatches = (int64_t)h;
+    return 0;
+}
+
 extern "C" {
+
+int lbk_selftest_div_const_f64(const uint64_t *bits, int64_t n, int64_t *mismatches) { return check_div_const<double, unsigned long long>(reinterpret_cast<const unsigned long long *>(bits), n, mismatches); }
+int lbk_selftest_div_const_f32(const uint32_t *bits, int64_t n, int64_t *mismatches) { return check_div_const<float, unsigned int>(bits, n, mismatches); }
 
 int lbk_equilibrium1_f32(float rho, float ux, float uy, float *out9) { return equilibrium1<float>(rho, ux, uy, out9); }
 int lbk_equilibrium1_f64(double rho, double ux, double uy, double *out9) { return equilibrium1<double>(rho, ux, uy, out9); }

@@ -32,7 +32,7 @@ struct lb_lattice {
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     NbrHost nbr[LB_NUM_DIRS];
     std::map<std::pair<int64_t, uint64_t>, char *> ipc_open;   // (pid, remote base) -> mapped base
-    int rows_per_tile = 8;
+    int rows_per_tile = 4;
     int64_t steps = 0;
     int64_t launches = 0;
     // shear probe

@@ -221,8 +221,46 @@ __device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__r
 }
 
 // Resident CTAs per SM the register allocation is tuned for (x 256 threads).
+// Resident CTAs per SM the register allocation targets (x 256 threads).  With the 3-operation
+// constant divisions the EXACT fp64 kernel fits 62 registers without spills, so every variant
+// runs 4 CTAs (32 warps) per SM.  (Measured alternatives at 4096^2 fp64 EXACT: 3 CTAs 44.0-44.3,
+// 4 CTAs 44.0-45.0, 2 CTAs 36-38, software-prefetched rows 44.5-45.2 GLUPS -- all within noise of
+// the HBM roofline except 2 CTAs, so the simplest loop is kept.)
+#ifndef LBM_EXACT_MINB
+#define LBM_EXACT_MINB 4
+#endif
+#ifndef LBM_FAST_MINB
+#define LBM_FAST_MINB 4
+#endif
+#ifndef LBM_PREFETCH
+#define LBM_PREFETCH 0
+#endif
 template <typename T, bool EXACT>
-__host__ __device__ constexpr int min_ctas_per_sm() { return (sizeof(T) == 8 && EXACT) ? 3 : 4; }
+__host__ __device__ constexpr int min_ctas_per_sm() { return (sizeof(T) == 8 && EXACT) ? LBM_EXACT_MINB : LBM_FAST_MINB; }
+
+// Interior cell, split into its load and its compute+store half so that the row loop can be
+// software-pipelined (loads of row k+1 in flight while row k is collided).
+template <typename T>
+__device__ __forceinline__ void interior_load(const StepParams<T> &p, const char *sp, T (&f)[9])
+{
+#pragma unroll
+    for (int i = 0; i < 9; ++i) f[i] = *reinterpret_cast<const T *>(sp + p.ld_off[i]);
+}
+template <typename T, int BC, bool EXACT, bool COLLIDE>
+__device__ __forceinline__ void interior_finish(const StepParams<T> &p, T *dp, T (&f)[9])
+{
+    if (COLLIDE) {
+        if (BC >= BC_SF_COUETTE)
+            sf_collide<T>(f, p.omega);
+        else
+            d2q9_collide<T, EXACT>(f, p.omega);
+    }
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        *dp = f[i];
+        dp += p.pop_stride;
+    }
+}
 
 template <typename T, int BC, bool EXACT, bool COLLIDE>
 __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kernel(const __grid_constant__ StepParams<T> p)
@@ -273,9 +311,34 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
         const int l = lt * TILE_L + threadIdx.x;
         const int k0 = max(kt * p.rows_per_tile, 1);
         const int k1 = min(kt * p.rows_per_tile + p.rows_per_tile, p.lnx - 1);
-        if (l >= 1 && l < p.lny - 1) {
+        if (l >= 1 && l < p.lny - 1 && k0 < k1) {
+            const long long c0 = (long long)(k0 + 1) * p.pitch + (l + PAD_L);
+            const char *sp = reinterpret_cast<const char *>(src + c0);
+            T *dp = dst + c0;
+            const long long row_bytes = p.pitch * (long long)sizeof(T);
+#if LBM_PREFETCH
+            T cur[9];
+            interior_load<T>(p, sp, cur);
 #pragma unroll 1
-            for (int k = k0; k < k1; ++k) update_cell<T, BC, EXACT, COLLIDE, false>(p, src, dst, par ^ 1, k, l);
+            for (int k = k0; k < k1; ++k) {
+                T nxt[9];
+                sp += row_bytes;
+                if (k + 1 < k1) interior_load<T>(p, sp, nxt);
+                interior_finish<T, BC, EXACT, COLLIDE>(p, dp, cur);
+                dp += p.pitch;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) cur[i] = nxt[i];
+            }
+#else
+#pragma unroll 1
+            for (int k = k0; k < k1; ++k) {
+                T f[9];
+                interior_load<T>(p, sp, f);
+                interior_finish<T, BC, EXACT, COLLIDE>(p, dp, f);
+                sp += row_bytes;
+                dp += p.pitch;
+            }
+#endif
         }
         __syncthreads();
     }

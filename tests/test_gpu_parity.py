@@ -181,3 +181,26 @@ def test_full_size_properties_4096():
     assert np.array_equal(uy1[:, 0], uy1[:, n // 2])
     assert np.array_equal(uy1[:, 0], uy1[:, n - 1])
     del rng
+
+
+def test_exact_constant_division():
+    """The EXACT kernel replaces x/9 and x/6 by a 3-operation sequence proven correctly rounded
+    (d2q9_math.cuh: rn_div_const); check it against the IEEE division on 2^26 random bit patterns per
+    type plus edge cases (zeros, subnormals, binade edges, huge, inf, nan, values around 1)."""
+    import ctypes
+    lb = require_gpu()
+    from latticeboltzmann_b200 import _lib as L
+    lib = L.load()
+    rng = np.random.default_rng(7)
+    n = 1 << 26
+    for dt, ut, fn in ((np.float64, np.uint64, lib.lbk_selftest_div_const_f64), (np.float32, np.uint32, lib.lbk_selftest_div_const_f32)):
+        info = np.finfo(dt)
+        edge = np.array([0.0, -0.0, info.tiny, -info.tiny, info.tiny / 8, info.max, -info.max, np.inf, -np.inf, np.nan,
+                         1.0, 9.0, 6.0, 1 - info.epsneg, 1 + info.eps, 2.0, 4 - 2 * info.eps, 0.1, 1 / 3, 4 / 9, 1e-30, 1e30], dtype=dt)
+        near = (1 + 0.1 * rng.standard_normal(n // 4)).astype(dt)            # densities
+        small = (1e-3 * rng.standard_normal(n // 4)).astype(dt)              # u.u magnitudes
+        bits = rng.integers(0, np.iinfo(ut).max, size=n // 2, dtype=ut, endpoint=True)
+        allbits = np.ascontiguousarray(np.concatenate([edge.view(ut), near.view(ut), small.view(ut), bits]))
+        bad = ctypes.c_int64(-1)
+        L.check(fn(L.np_ptr(allbits), allbits.size, ctypes.byref(bad)))
+        assert bad.value == 0, (dt, bad.value)

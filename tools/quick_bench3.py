@@ -1,0 +1,10 @@
+import json, os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from tools.quick_bench import run
+n = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+tag = os.environ.get("LBM_NATIVE_LIB", "product").split("/")[-1]
+for dtype in ("float64",):
+    for arith in ("exact", "fast"):
+        for rows in (4, 8):
+            m, gbs = run(n, dtype, arith, rows)
+            print(json.dumps({"lib": tag, "n": n, "dtype": dtype, "arith": arith, "rows": rows, "mlups": round(m, 1), "GBs": round(gbs, 1)}), flush=True)
