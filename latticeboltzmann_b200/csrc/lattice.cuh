@@ -75,6 +75,7 @@ struct StepParams {
     T sf_uw6;                // simple_flows: (1/6)*uw, evaluated in double on the host (PoiseuilleFlow.py:73-74)
     T rho_in, rho_out;       // simple_flows Poiseuille (PoiseuilleFlow.py:134-135)
     int all_rim;             // 1: every cell takes the general (rim) path, no interior tiles
+    int sys_scope;           // 1: some neighbour is on another device / process (system-scope fences)
     // Byte offsets relative to a cell's own slot, precomputed on the host so that the kernel adds
     // them straight from the constant bank (no registers): ld_off[i] addresses the pull source
     // (i, k - cx_i, l - cy_i).

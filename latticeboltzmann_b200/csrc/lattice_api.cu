@@ -90,9 +90,11 @@ StepParams<T> make_params(lb_lattice *L)
     for (int i = 0; i < 9; ++i) {
         p.ld_off[i] = (long long)sizeof(T) * (i * L->pop_stride - cx_of(i) * L->pitch - cy_of(i));
     }
+    p.sys_scope = 0;
     for (int d = 0; d < LB_NUM_DIRS; ++d) {
         const NbrHost &n = L->nbr[d];
         if (!n.connected) continue;
+        if (n.exp.pid != (int64_t)getpid() || n.exp.device != L->cfg.device) p.sys_scope = 1;
         p.nbr[d].buf[0] = reinterpret_cast<T *>(n.base);
         p.nbr[d].buf[1] = reinterpret_cast<T *>(n.base + n.exp.buf_bytes);
         p.nbr[d].ycol[0] = reinterpret_cast<T *>(n.base + n.exp.ycol_offset);

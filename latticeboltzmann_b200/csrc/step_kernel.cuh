@@ -38,9 +38,19 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v)
 {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// Fence at the scope the block's neighbours need: system scope only when a neighbour lives on
+// another GPU / in another process; a self-closed ring or blocks sharing the device need gpu scope
+// (a system-scope fence costs microseconds, which is the whole budget of a small lattice's step).
+__device__ __forceinline__ void halo_fence(int sys_scope)
+{
+    if (sys_scope)
+        __threadfence_system();
+    else
+        __threadfence();
 }
 __device__ __forceinline__ unsigned long long global_timer_ns()
 {
@@ -276,7 +286,7 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
         // Wait for the 8 neighbours' step-(n-1) halos (and for them to be done
         // reading the ghosts this step overwrites).
         if (threadIdx.x < NUM_DIRS) {
-            if (*(volatile unsigned int *)&st->error == 0) {
+            if (ld_acquire_sys(&st->flag_in[threadIdx.x]) < step && *(volatile unsigned int *)&st->error == 0) {
                 const unsigned long long t0 = global_timer_ns();
                 while (ld_acquire_sys(&st->flag_in[threadIdx.x]) < step) {
                     if (global_timer_ns() - t0 > HALO_TIMEOUT_NS) {
@@ -295,13 +305,13 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
         }
         __syncthreads();
         if (threadIdx.x == 0) {
-            __threadfence_system();
+            halo_fence(p.sys_scope);                  // this CTA's pushes are visible before it is counted
             const unsigned int prev = atomicAdd(&st->edge_done, 1u);
             if (prev == (unsigned int)p.n_rim_ctas - 1u) {
                 st->edge_done = 0u;
-                __threadfence_system();
+                halo_fence(p.sys_scope);              // fence + relaxed stores = release of all rim CTAs' pushes
 #pragma unroll
-                for (int d = 0; d < NUM_DIRS; ++d) st_release_sys(p.nbr[d].flag_in + dir_opp(d), step + 1ull);
+                for (int d = 0; d < NUM_DIRS; ++d) st_relaxed_sys(p.nbr[d].flag_in + dir_opp(d), step + 1ull);
             }
         }
     } else {
