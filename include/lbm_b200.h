@@ -170,6 +170,11 @@ LB_API int lb_probe_shear_read(lb_lattice *lat, void *out, int64_t n);
 
 /* Tuning: rows of the lattice handled by one CTA (default 4).                  */
 LB_API int lb_set_rows_per_tile(lb_lattice *lat, int rows);
+/* How long a rim CTA waits for a neighbour's halo flag before the lattice is marked failed
+ * (lb_health -> LB_ERR_HALO_TIMEOUT) instead of hanging the GPU.  Default 20 s.            */
+LB_API int lb_set_halo_timeout_ms(lb_lattice *lat, int64_t ms);
+/* lb_step replays a CUDA graph of 64 fused steps for long runs (default on).                */
+LB_API int lb_set_use_graph(lb_lattice *lat, int on);
 /* Geometry queries (elements). */
 LB_API int64_t lb_pitch(lb_lattice *lat);
 LB_API int64_t lb_pop_stride(lb_lattice *lat);

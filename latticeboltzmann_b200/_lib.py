@@ -69,6 +69,8 @@ SYMBOLS = {
     "lb_probe_shear_enable": (ctypes.c_int, [c_vp, c_i64, c_vp, c_i64]),
     "lb_probe_shear_read": (ctypes.c_int, [c_vp, c_vp, c_i64]),
     "lb_set_rows_per_tile": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "lb_set_halo_timeout_ms": (ctypes.c_int, [c_vp, c_i64]),
+    "lb_set_use_graph": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "lb_pitch": (c_i64, [c_vp]),
     "lb_pop_stride": (c_i64, [c_vp]),
     "lb_kernel_launches": (ctypes.c_int, [c_vp, _P(c_i64)]),

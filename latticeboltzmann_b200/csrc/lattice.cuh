@@ -76,6 +76,7 @@ struct StepParams {
     T rho_in, rho_out;       // simple_flows Poiseuille (PoiseuilleFlow.py:134-135)
     int all_rim;             // 1: every cell takes the general (rim) path, no interior tiles
     int sys_scope;           // 1: some neighbour is on another device / process (system-scope fences)
+    unsigned long long halo_timeout_ns;   // give up waiting for a neighbour's flag after this long
     // Byte offsets relative to a cell's own slot, precomputed on the host so that the kernel adds
     // them straight from the constant bank (no registers): ld_off[i] addresses the pull source
     // (i, k - cx_i, l - cy_i).

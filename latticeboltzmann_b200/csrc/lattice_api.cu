@@ -33,6 +33,12 @@ struct lb_lattice {
     NbrHost nbr[LB_NUM_DIRS];
     std::map<std::pair<int64_t, uint64_t>, char *> ipc_open;   // (pid, remote base) -> mapped base
     int rows_per_tile = 4;
+    unsigned long long halo_timeout_ns = 20ull * 1000 * 1000 * 1000;
+    // CUDA graph of GRAPH_STEPS fused steps (launch arguments are step-independent)
+    cudaGraphExec_t graph_exec = nullptr;
+    cudaStream_t graph_stream = nullptr;
+    int graph_rows_per_tile = 0;
+    bool use_graph = true;
     int64_t steps = 0;
     int64_t launches = 0;
     // shear probe
@@ -49,6 +55,12 @@ struct lb_lattice {
 namespace {
 
 int grid_for(long long n, int block);
+
+void drop_graph(lb_lattice *L)
+{
+    if (L->graph_exec) cudaGraphExecDestroy(L->graph_exec);
+    L->graph_exec = nullptr;
+}
 
 DevState *dev_state(lb_lattice *L) { return reinterpret_cast<DevState *>(L->base + L->state_off); }
 
@@ -91,6 +103,7 @@ StepParams<T> make_params(lb_lattice *L)
         p.ld_off[i] = (long long)sizeof(T) * (i * L->pop_stride - cx_of(i) * L->pitch - cy_of(i));
     }
     p.sys_scope = 0;
+    p.halo_timeout_ns = L->halo_timeout_ns;
     for (int d = 0; d < LB_NUM_DIRS; ++d) {
         const NbrHost &n = L->nbr[d];
         if (!n.connected) continue;
@@ -248,6 +261,7 @@ int lb_destroy(lb_lattice *L)
     cudaSetDevice(L->cfg.device);
     // L->stream may be borrowed (another block's or torch's) and already gone: sync the device.
     cudaDeviceSynchronize();
+    drop_graph(L);
     for (auto &kv : L->ipc_open) cudaIpcCloseMemHandle(kv.second);
     if (L->d_uyk) cudaFree(L->d_uyk);
     if (L->d_series) cudaFree(L->d_series);
@@ -279,6 +293,21 @@ int lb_set_rows_per_tile(lb_lattice *L, int rows)
 {
     if (!L || rows < 1) return lbm_fail(LB_ERR_INVALID, "rows_per_tile must be >= 1");
     L->rows_per_tile = rows;
+    return 0;
+}
+
+int lb_set_halo_timeout_ms(lb_lattice *L, int64_t ms)
+{
+    if (!L || ms < 1) return lbm_fail(LB_ERR_INVALID, "timeout must be >= 1 ms");
+    L->halo_timeout_ns = (unsigned long long)ms * 1000000ull;
+    drop_graph(L);      // the timeout is a launch argument
+    return 0;
+}
+
+int lb_set_use_graph(lb_lattice *L, int on)
+{
+    if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
+    L->use_graph = on != 0;
     return 0;
 }
 
@@ -353,6 +382,7 @@ int lb_connect(lb_lattice *L, int dir, const lb_export *nb)
             L->ipc_open[key] = base;
         }
     }
+    drop_graph(L);
     L->nbr[dir].connected = true;
     L->nbr[dir].base = base;
     L->nbr[dir].exp = *nb;
@@ -420,12 +450,53 @@ int lb_init_equilibrium(lb_lattice *L, const void *rho, const void *ux, const vo
     return 0;
 }
 
+namespace {
+constexpr int GRAPH_STEPS = 64;
+
+// One launch of the instantiated graph = GRAPH_STEPS fused steps.  Valid because the kernel reads the
+// step number (buffer parity, flag values) from device memory: every launch has identical arguments.
+int ensure_graph(lb_lattice *L)
+{
+    if (L->graph_exec && L->graph_stream == L->stream && L->graph_rows_per_tile == L->rows_per_tile) return 0;
+    drop_graph(L);
+    cudaGraph_t g = nullptr;
+    LBM_CUDA(cudaStreamBeginCapture(L->stream, cudaStreamCaptureModeThreadLocal));
+    int r = 0;
+    for (int s = 0; s < GRAPH_STEPS && !r; ++s) r = L->cfg.dtype == LB_F64 ? launch_step<double>(L, true) : launch_step<float>(L, true);
+    cudaError_t e = cudaStreamEndCapture(L->stream, &g);
+    if (r || e != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return r ? r : lbm_fail(LB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    }
+    e = cudaGraphInstantiate(&L->graph_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        L->graph_exec = nullptr;
+        return lbm_fail(LB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    L->graph_stream = L->stream;
+    L->graph_rows_per_tile = L->rows_per_tile;
+    return 0;
+}
+}  // namespace
+
 int lb_step(lb_lattice *L, int64_t nsteps)
 {
     if (int r = check_ready(L)) return r;
     if (nsteps < 0) return lbm_fail(LB_ERR_INVALID, "nsteps < 0");
     LBM_CUDA(cudaSetDevice(L->cfg.device));
     const bool sf = L->cfg.boundary >= LB_SF_COUETTE;
+    // Long runs of plain fused steps replay a CUDA graph (one host call per GRAPH_STEPS launches).
+    if (L->use_graph && !sf && !L->d_series && nsteps >= 2 * GRAPH_STEPS) {
+        if (int r = ensure_graph(L)) return r;
+        while (nsteps >= GRAPH_STEPS) {
+            LBM_CUDA(cudaGraphLaunch(L->graph_exec, L->stream));
+            L->launches += GRAPH_STEPS;
+            L->steps += GRAPH_STEPS;
+            nsteps -= GRAPH_STEPS;
+        }
+    }
     for (int64_t s = 0; s < nsteps; ++s) {
         if (sf) launch_sf_prologue<double>(L);
         // Couette collides BEFORE streaming (prologue), so its fused pass streams + reflects only.

@@ -30,7 +30,6 @@ namespace lbm {
 
 enum BoundaryKind { BC_PERIODIC = 0, BC_CAVITY = 1, BC_CAVITY_XPERIODIC = 2, BC_SF_COUETTE = 3, BC_SF_POISEUILLE = 4, BC_SF_SLIDING_LID = 5 };
 
-constexpr unsigned long long HALO_TIMEOUT_NS = 20ull * 1000ull * 1000ull * 1000ull;
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
@@ -289,7 +288,7 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
             if (ld_acquire_sys(&st->flag_in[threadIdx.x]) < step && *(volatile unsigned int *)&st->error == 0) {
                 const unsigned long long t0 = global_timer_ns();
                 while (ld_acquire_sys(&st->flag_in[threadIdx.x]) < step) {
-                    if (global_timer_ns() - t0 > HALO_TIMEOUT_NS) {
+                    if (global_timer_ns() - t0 > p.halo_timeout_ns) {
                         atomicExch(&st->error, 1u);
                         break;
                     }

@@ -66,6 +66,12 @@ class Block:
     def set_rows_per_tile(self, rows):
         check(self.lib.lb_set_rows_per_tile(self.h, rows))
 
+    def set_halo_timeout_ms(self, ms):
+        check(self.lib.lb_set_halo_timeout_ms(self.h, int(ms)))
+
+    def set_use_graph(self, on):
+        check(self.lib.lb_set_use_graph(self.h, int(bool(on))))
+
     # -- state ----------------------------------------------------------------
     def _host(self, a, shape):
         a = np.ascontiguousarray(a, dtype=self.dtype)

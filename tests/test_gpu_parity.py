@@ -204,3 +204,37 @@ def test_exact_constant_division():
         bad = ctypes.c_int64(-1)
         L.check(fn(L.np_ptr(allbits), allbits.size, ctypes.byref(bad)))
         assert bad.value == 0, (dt, bad.value)
+
+
+def test_halo_timeout_is_reported_not_hung():
+    """A neighbour that never posts its halo flag must surface as LB_ERR_HALO_TIMEOUT, not a hung GPU."""
+    lb = require_gpu()
+    lat = lb.Lattice(64, 32, "cavity", omega=1.0, ndx=2, ndy=1)
+    lat.init_equilibrium()
+    a, b = lat.blocks
+    a.set_halo_timeout_ms(200)
+    a.step(1)                 # step 0 needs flags >= 0: fine
+    a.step(1)                 # step 1 needs b's flag >= 1, but b never stepped
+    with pytest.raises(lb.LbmError, match="halo flag wait timed out"):
+        a.health()
+    lat.close()
+
+
+def test_graph_replay_equals_single_launches():
+    """lb_step replays a CUDA graph of 64 fused steps for long runs; same bits as step-by-step launches."""
+    lb = require_gpu()
+    f0 = orc.perturbed_state(70, 530, seed=5)
+    outs = []
+    for use_graph in (True, False):
+        lat = lb.Lattice(70, 530, "cavity", omega=1.7)
+        lat.blocks[0].set_use_graph(use_graph)
+        lat.upload(f0)
+        lat.step(64 * 3 + 17)
+        outs.append(lat.download())
+        assert lat.kernel_launches >= 64 * 3 + 17
+        lat.health()
+        lat.close()
+    assert np.array_equal(outs[0], outs[1])
+    ref = f0.copy()
+    orc.cavity_run(ref, 1.7, 64 * 3 + 17)
+    assert np.array_equal(outs[0], ref)
