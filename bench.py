@@ -189,7 +189,7 @@ def e2e_host_step(lat, steps):
 
     def one():
         if single:                                             # slab-pipelined: H2D, compute, D2H overlap
-            check(lib.lb_step_host(blk.h, ptr, ptr, 32))
+            check(lib.lb_step_host(blk.h, ptr, ptr, 128))
             return
         check(lib.lb_upload_f(blk.h, ptr))                     # H2D (synchronous on return)
         dist.barrier()
@@ -258,6 +258,7 @@ def main():
     if world != args.gpus:
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N > 1)" % (args.gpus, world))
     rank, world, local_rank = D.init_process_group("nccl")
+    numa = D.bind_to_gpu_numa(local_rank) if world > 1 else None      # pinned e2e buffers next to their GPU
     lat = D.DistributedLattice(nx, ny, ndx, ndy, "cavity", omega=omega, u_wall=0.1, dtype=np.float64,
                                arith=args.arith, device=local_rank, rows_per_tile=args.rows_per_tile or None)
     lat.init_equilibrium()
@@ -298,7 +299,7 @@ def main():
             sec, nbytes = e2e_host_step(lat, args.e2e_steps)
             sec = D.max_over_ranks(sec)
             e2e = {"value": cells / sec / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
-                   "steps": args.e2e_steps, "path": ("lb_step_host: pinned host f[9,nx,ny] in/out every step, 32 slabs, H2D/compute/D2H overlapped" if world == 1 else
+                   "steps": args.e2e_steps, "path": ("lb_step_host: pinned host f[9,nx,ny] in/out every step, 128 slabs, H2D/compute/D2H overlapped" if world == 1 else
                             "lb_upload_f + lb_halo_refresh + lb_step(1) + lb_download_f on pinned host f[9,lnx,lny] per rank; bytes are per rank")}
         except Exception as exc:      # reported, never hidden
             e2e = {"value": None, "unit": "MLUPS", "error": repr(exc)}
@@ -315,6 +316,7 @@ def main():
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc, "nx": nx, "ny": ny, "ndx": ndx, "ndy": ndy, "omega": omega, "u0": 0.1,
                            "arith": args.arith, "halo": "in-kernel peer stores over NVLink (CUDA IPC), device-side flags",
+                           "numa_bound_cpus": (len(numa) if numa else None),
                            "l2": "inputs larger than L2 (%.1f GB per buffer per GPU, A/B ping-pong)" % (9 * b.lnx * b.lny * 8 / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,

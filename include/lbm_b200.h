@@ -168,7 +168,7 @@ LB_API int lb_moments(lb_lattice *lat, void *rho, void *ux, void *uy);
 LB_API int lb_probe_shear_enable(lb_lattice *lat, int64_t l_probe_global, const void *uy_k, int64_t capacity);
 LB_API int lb_probe_shear_read(lb_lattice *lat, void *out, int64_t n);
 
-/* Tuning: rows of the lattice handled by one CTA (default 4).                  */
+/* Tuning: rows of the lattice handled by one CTA (default 4 for fp64, 8 for fp32).                  */
 LB_API int lb_set_rows_per_tile(lb_lattice *lat, int rows);
 /* How long a rim CTA waits for a neighbour's halo flag before the lattice is marked failed
  * (lb_health -> LB_ERR_HALO_TIMEOUT) instead of hanging the GPU.  Default 20 s.            */

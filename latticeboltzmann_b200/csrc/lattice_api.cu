@@ -249,6 +249,7 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     LBM_CUDA(cudaEventCreate(&L->ev1));
     LBM_CUDA(cudaMemsetAsync(L->base, 0, L->total_bytes, L->stream));
     LBM_CUDA(cudaStreamSynchronize(L->stream));
+    L->rows_per_tile = cfg->dtype == LB_F64 ? 4 : 8;     // measured optima
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
     *out = L;

@@ -241,9 +241,6 @@ __device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__r
 #ifndef LBM_FAST_MINB
 #define LBM_FAST_MINB 4
 #endif
-#ifndef LBM_PREFETCH
-#define LBM_PREFETCH 0
-#endif
 template <typename T, bool EXACT>
 __host__ __device__ constexpr int min_ctas_per_sm() { return (sizeof(T) == 8 && EXACT) ? LBM_EXACT_MINB : LBM_FAST_MINB; }
 
@@ -271,6 +268,57 @@ __device__ __forceinline__ void interior_finish(const StepParams<T> &p, T *dp, T
     }
 }
 
+// ---- rim CTAs: the block's perimeter cells, ghost reads, halo pushes ----
+template <typename T, int BC, bool EXACT, bool COLLIDE>
+__device__ __forceinline__ void rim_cta(const StepParams<T> &p, DevState *st, unsigned long long step, const T *__restrict__ src,
+                                        T *__restrict__ dst, int par)
+{
+    // Wait for the 8 neighbours' step-(n-1) halos (and for them to be done reading the ghosts this
+    // step overwrites).
+    if (threadIdx.x < NUM_DIRS) {
+        if (ld_acquire_sys(&st->flag_in[threadIdx.x]) < step && *(volatile unsigned int *)&st->error == 0) {
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_sys(&st->flag_in[threadIdx.x]) < step) {
+                if (global_timer_ns() - t0 > p.halo_timeout_ns) {
+                    atomicExch(&st->error, 1u);
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const long long t = (long long)blockIdx.x * TILE_L + threadIdx.x;
+    if (t < p.n_perimeter) {
+        int k, l;
+        decode_perimeter<T>(p, t, k, l);
+        update_cell<T, BC, EXACT, COLLIDE, true>(p, src, dst, par ^ 1, k, l);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        halo_fence(p.sys_scope);                  // this CTA's pushes are visible before it is counted
+        const unsigned int prev = atomicAdd(&st->edge_done, 1u);
+        if (prev == (unsigned int)p.n_rim_ctas - 1u) {
+            st->edge_done = 0u;
+            halo_fence(p.sys_scope);              // fence + relaxed stores = release of all rim CTAs' pushes
+#pragma unroll
+            for (int d = 0; d < NUM_DIRS; ++d) st_relaxed_sys(p.nbr[d].flag_in + dir_opp(d), step + 1ull);
+        }
+    }
+}
+
+// The last CTA of the launch publishes the new step count (read by the next launch -- which makes
+// the launch arguments step-independent and the whole loop CUDA-graph replayable).
+__device__ __forceinline__ void publish_step(DevState *st, unsigned long long step)
+{
+    if (threadIdx.x == 0) {
+        const unsigned int prev = atomicAdd(&st->all_done, 1u);
+        if (prev == gridDim.x - 1u) {
+            st->all_done = 0u;
+            *(volatile unsigned long long *)&st->step = step + 1ull;
+        }
+    }
+}
+
 template <typename T, int BC, bool EXACT, bool COLLIDE>
 __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kernel(const __grid_constant__ StepParams<T> p)
 {
@@ -281,38 +329,7 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
     T *__restrict__ dst = p.buf[par ^ 1];
 
     if ((int)blockIdx.x < p.n_rim_ctas) {
-        // ---- rim CTAs: the block's perimeter cells, ghost reads, halo pushes ----
-        // Wait for the 8 neighbours' step-(n-1) halos (and for them to be done
-        // reading the ghosts this step overwrites).
-        if (threadIdx.x < NUM_DIRS) {
-            if (ld_acquire_sys(&st->flag_in[threadIdx.x]) < step && *(volatile unsigned int *)&st->error == 0) {
-                const unsigned long long t0 = global_timer_ns();
-                while (ld_acquire_sys(&st->flag_in[threadIdx.x]) < step) {
-                    if (global_timer_ns() - t0 > p.halo_timeout_ns) {
-                        atomicExch(&st->error, 1u);
-                        break;
-                    }
-                }
-            }
-        }
-        __syncthreads();
-        const long long t = (long long)blockIdx.x * TILE_L + threadIdx.x;
-        if (t < p.n_perimeter) {
-            int k, l;
-            decode_perimeter<T>(p, t, k, l);
-            update_cell<T, BC, EXACT, COLLIDE, true>(p, src, dst, par ^ 1, k, l);
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) {
-            halo_fence(p.sys_scope);                  // this CTA's pushes are visible before it is counted
-            const unsigned int prev = atomicAdd(&st->edge_done, 1u);
-            if (prev == (unsigned int)p.n_rim_ctas - 1u) {
-                st->edge_done = 0u;
-                halo_fence(p.sys_scope);              // fence + relaxed stores = release of all rim CTAs' pushes
-#pragma unroll
-                for (int d = 0; d < NUM_DIRS; ++d) st_relaxed_sys(p.nbr[d].flag_in + dir_opp(d), step + 1ull);
-            }
-        }
+        rim_cta<T, BC, EXACT, COLLIDE>(p, st, step, src, dst, par);
     } else {
         // ---- interior CTAs: rows_per_tile x 256 cells, no ghosts, no predicates ----
         const int tile = (int)blockIdx.x - p.n_rim_ctas;
@@ -325,42 +342,34 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
             const char *sp = reinterpret_cast<const char *>(src + c0);
             T *dp = dst + c0;
             const long long row_bytes = p.pitch * (long long)sizeof(T);
-#if LBM_PREFETCH
-            T cur[9];
-            interior_load<T>(p, sp, cur);
+            int k = k0;
+            if (sizeof(T) == 4) {
+                // fp32 moves half the bytes per lane, so one row per iteration leaves too few bytes in
+                // flight per warp (measured 77.8 GLUPS); two rows per iteration = 18 loads in flight per
+                // thread, the same 72 B as fp64 (85.8 GLUPS).  For fp64 the single-row loop is as fast or faster.
 #pragma unroll 1
-            for (int k = k0; k < k1; ++k) {
-                T nxt[9];
-                sp += row_bytes;
-                if (k + 1 < k1) interior_load<T>(p, sp, nxt);
-                interior_finish<T, BC, EXACT, COLLIDE>(p, dp, cur);
-                dp += p.pitch;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) cur[i] = nxt[i];
+                for (; k + 1 < k1; k += 2) {
+                    T fa[9], fb[9];
+                    interior_load<T>(p, sp, fa);
+                    interior_load<T>(p, sp + row_bytes, fb);
+                    interior_finish<T, BC, EXACT, COLLIDE>(p, dp, fa);
+                    interior_finish<T, BC, EXACT, COLLIDE>(p, dp + p.pitch, fb);
+                    sp += 2 * row_bytes;
+                    dp += 2 * p.pitch;
+                }
             }
-#else
 #pragma unroll 1
-            for (int k = k0; k < k1; ++k) {
+            for (; k < k1; ++k) {
                 T f[9];
                 interior_load<T>(p, sp, f);
                 interior_finish<T, BC, EXACT, COLLIDE>(p, dp, f);
                 sp += row_bytes;
                 dp += p.pitch;
             }
-#endif
         }
         __syncthreads();
     }
-    // The last CTA of the launch publishes the new step count (read by the next
-    // launch -- which makes the launch arguments step-independent and the whole
-    // loop CUDA-graph replayable).
-    if (threadIdx.x == 0) {
-        const unsigned int prev = atomicAdd(&st->all_done, 1u);
-        if (prev == gridDim.x - 1u) {
-            st->all_done = 0u;
-            *(volatile unsigned long long *)&st->step = step + 1ull;
-        }
-    }
+    publish_step(st, step);
 }
 
 // Rows [k_lo, k_hi) of one step through the general (rim) cell path, without the flag protocol and

@@ -47,6 +47,26 @@ def init_process_group(backend=None):
     return rank, world, local_rank
 
 
+def bind_to_gpu_numa(device_index):
+    """Pin this process to the CPUs NVML reports as local to its GPU, so that pinned host buffers
+    (first touch) and the launch thread sit on the GPU's NUMA node.  Best effort: returns the CPU
+    set applied, or None if NVML / the affinity call is unavailable."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(device_index))
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63) // 64)
+        cpus = {64 * w + b for w, mask in enumerate(words) for b in range(64) if (mask >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return cpus
+    except Exception:
+        pass
+    return None
+
+
 def exchange_blobs(blob, group=None):
     """All-gather one bytes object per rank (rank order)."""
     dist = _dist()

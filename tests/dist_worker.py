@@ -38,32 +38,34 @@ def ghost_slices(d, lnx, lny, ghost):
     return sx, sy
 
 
+def opposite(d):
+    return d ^ 1 if d < 4 else 11 - d          # 0<->1, 2<->3, 4<->7, 5<->6 (csrc/lattice.cuh dir_opp)
+
+
 def exchange(G, decomp, rank, lnx, lny):
-    """Ghost-frame exchange over torch.distributed p2p (stands in for the kernel's peer stores)."""
+    """Ghost-frame exchange over torch.distributed p2p (stands in for the kernel's peer stores):
+    for every direction slot d, send the rim strip that leaves through d to neighbour(d) and
+    receive, from neighbour(opposite(d)), the strip that lands on my opposite-side ghost."""
     import torch
-    reqs, recvs = [], []
+    sends, recvs = [], []
     for d in range(8):
-        nb = decomp.neighbour(rank, d)
+        pops = list(LEAVING[d])
         sx, sy = ghost_slices(d, lnx, lny, ghost=False)
-        out = np.ascontiguousarray(G[list(LEAVING[d])][:, sx, sy])
-        src = decomp.neighbour(rank, d ^ 1 if d < 4 else 11 - d)   # opposite slot
-        od = d ^ 1 if d < 4 else 11 - d
         gx, gy = ghost_slices(d, lnx, lny, ghost=True)
-        buf = torch.empty(out.shape if True else None, dtype=torch.float64)
-        # the strip arriving on my `-d` side comes from the neighbour in direction opp(d), which sent its `d` strip
-        shape = G[list(LEAVING[d])][:, gx, gy].shape
-        buf = torch.empty(shape, dtype=torch.float64)
-        if nb == rank and src == rank:
-            G[np.ix_(list(LEAVING[d]), range(gx.start, gx.stop), range(gy.start, gy.stop))] = out
+        out = np.ascontiguousarray(G[pops][:, sx, sy])
+        dst, src = decomp.neighbour(rank, d), decomp.neighbour(rank, opposite(d))
+        target = np.ix_(pops, range(gx.start, gx.stop), range(gy.start, gy.stop))
+        if dst == rank and src == rank:            # ring closed on this rank
+            G[target] = out
             continue
-        reqs.append(dist.isend(torch.from_numpy(out), nb, tag=d))
-        recvs.append((dist.irecv(buf, src, tag=d), buf, d, gx, gy))
-        del od
-    for r in reqs:
+        buf = torch.empty(out.shape, dtype=torch.float64)
+        sends.append(dist.isend(torch.from_numpy(out), dst, tag=d))
+        recvs.append((dist.irecv(buf, src, tag=d), buf, target))
+    for r in sends:
         r.wait()
-    for r, buf, d, gx, gy in recvs:
+    for r, buf, target in recvs:
         r.wait()
-        G[np.ix_(list(LEAVING[d]), range(gx.start, gx.stop), range(gy.start, gy.stop))] = buf.numpy()
+        G[target] = buf.numpy()
 
 
 def block_step(G, blk, gnx, gny, omega, u0, boundary):
