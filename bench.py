@@ -146,8 +146,9 @@ def cpu_reference(nx_total, ny_total, omega, steps, warmup, cores=None):
     pd = 1
     while pd * pd < p:
         pd += 1
-    bx = int(min(2048, max(64, nx_total // pd)))
-    by = int(min(2048, max(64, ny_total // pd)))
+    cap = int(os.environ.get("LBM_REF_BLOCK", "2048"))        # tests shrink the sample
+    bx = int(min(cap, max(64, nx_total // pd)))
+    by = int(min(cap, max(64, ny_total // pd)))
     t = opt2_numpy.run_independent_blocks(p, bx, by, omega, warmup, steps)
     mlups = p * bx * by * steps / t / 1e6
     cpu_reference.last_ms_per_step = t / steps * 1e3

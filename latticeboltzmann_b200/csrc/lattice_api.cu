@@ -56,6 +56,26 @@ namespace {
 
 int grid_for(long long n, int block);
 
+// Make the lattice's device current for the duration of an API call and restore the caller's
+// (the library shares the process with torch, which tracks its own current device).
+struct DeviceGuard {
+    int prev = -1;
+    cudaError_t err;
+    explicit DeviceGuard(int dev)
+    {
+        cudaGetDevice(&prev);
+        err = prev == dev ? cudaSuccess : cudaSetDevice(dev);
+        if (prev == dev) prev = -1;
+    }
+    ~DeviceGuard()
+    {
+        if (prev >= 0) cudaSetDevice(prev);
+    }
+};
+#define LBM_ON_DEVICE(L)                    \
+    DeviceGuard lbm_guard_((L)->cfg.device); \
+    LBM_CUDA(lbm_guard_.err)
+
 void drop_graph(lb_lattice *L)
 {
     if (L->graph_exec) cudaGraphExecDestroy(L->graph_exec);
@@ -224,10 +244,13 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     }
     if (lb_device_count() <= 0)
         return lbm_fail(LB_ERR_NO_DEVICE, "no CUDA device visible: liblbm_b200 has no CPU fallback");
-    LBM_CUDA(cudaSetDevice(cfg->device));
-
     lb_lattice *L = new lb_lattice();
     L->cfg = *cfg;
+    DeviceGuard guard(cfg->device);
+    if (guard.err != cudaSuccess) {
+        delete L;
+        return lbm_fail(LB_ERR_CUDA, "cudaSetDevice(%d): %s", cfg->device, cudaGetErrorString(guard.err));
+    }
     L->elem = cfg->dtype == LB_F64 ? 8 : 4;
     // pitch: multiple of 32 elements (>= 128 B), room for PAD_L, lny cells and the upper ghost column.
     L->pitch = ((cfg->lny + PAD_L + 1 + 31) / 32) * 32;
@@ -241,14 +264,22 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     cudaError_t e = cudaMalloc(&L->base, L->total_bytes);
     if (e != cudaSuccess) {
         delete L;
-        return lbm_fail(LB_ERR_CUDA, "cudaMalloc(%zu bytes): %s", (size_t)(2 * (size_t)9 * (cfg->lnx + 2) * ((cfg->lny + 64)) * 8), cudaGetErrorString(e));
+        const size_t want = L->total_bytes;
+        delete L;
+        cudaGetLastError();
+        return lbm_fail(LB_ERR_CUDA, "cudaMalloc(%zu bytes for two f buffers): %s", want, cudaGetErrorString(e));
     }
-    LBM_CUDA(cudaStreamCreateWithFlags(&L->own_stream, cudaStreamNonBlocking));
+    e = cudaStreamCreateWithFlags(&L->own_stream, cudaStreamNonBlocking);
     L->stream = L->own_stream;
-    LBM_CUDA(cudaEventCreate(&L->ev0));
-    LBM_CUDA(cudaEventCreate(&L->ev1));
-    LBM_CUDA(cudaMemsetAsync(L->base, 0, L->total_bytes, L->stream));
-    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    if (e == cudaSuccess) e = cudaEventCreate(&L->ev0);
+    if (e == cudaSuccess) e = cudaEventCreate(&L->ev1);
+    if (e == cudaSuccess) e = cudaMemsetAsync(L->base, 0, L->total_bytes, L->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(L->stream);
+    if (e != cudaSuccess) {
+        cudaGetLastError();
+        lb_destroy(L);
+        return lbm_fail(LB_ERR_CUDA, "lattice set-up failed: %s", cudaGetErrorString(e));
+    }
     L->rows_per_tile = cfg->dtype == LB_F64 ? 4 : 8;     // measured optima
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
@@ -259,7 +290,7 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
 int lb_destroy(lb_lattice *L)
 {
     if (!L) return 0;
-    cudaSetDevice(L->cfg.device);
+    DeviceGuard guard(L->cfg.device);
     // L->stream may be borrowed (another block's or torch's) and already gone: sync the device.
     cudaDeviceSynchronize();
     drop_graph(L);
@@ -315,7 +346,7 @@ int lb_set_use_graph(lb_lattice *L, int on)
 int lb_sync(lb_lattice *L)
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     LBM_CUDA(cudaStreamSynchronize(L->stream));
     return 0;
 }
@@ -324,7 +355,7 @@ int lb_get_export(lb_lattice *L, lb_export *out)
 {
     if (!L || !out) return lbm_fail(LB_ERR_INVALID, "null argument");
     memset(out, 0, sizeof(*out));
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     cudaIpcMemHandle_t h;
     static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
     cudaError_t e = cudaIpcGetMemHandle(&h, L->base);
@@ -355,7 +386,7 @@ int lb_connect(lb_lattice *L, int dir, const lb_export *nb)
     // faces must match: x-neighbours share lny, y-neighbours share lnx
     if (dir_dy(dir) == 0 && nb->lny != L->cfg.lny) return lbm_fail(LB_ERR_INVALID, "x-neighbour with different lny");
     if (dir_dx(dir) == 0 && nb->lnx != L->cfg.lnx) return lbm_fail(LB_ERR_INVALID, "y-neighbour with different lnx");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     char *base = nullptr;
     if (nb->pid == (int64_t)getpid()) {
         base = reinterpret_cast<char *>(nb->local_base);
@@ -393,7 +424,7 @@ int lb_connect(lb_lattice *L, int dir, const lb_export *nb)
 int lb_halo_refresh(lb_lattice *L)
 {
     if (int r = check_ready(L)) return r;
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     const long long n_rim = 2 * (L->cfg.lnx + L->cfg.lny);
     if (L->cfg.dtype == LB_F64)
         halo_refresh_kernel<double><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(make_params<double>(L), 0, (int)L->cfg.lnx);
@@ -407,7 +438,7 @@ int lb_halo_refresh(lb_lattice *L)
 static int copy_f(lb_lattice *L, void *host, bool upload)
 {
     if (!L || !host) return lbm_fail(LB_ERR_INVALID, "null argument");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     const size_t e = L->elem;
     char *cur = L->base + (L->steps & 1) * L->buf_bytes;
     const size_t row = (size_t)L->cfg.lny * e;
@@ -429,7 +460,7 @@ int lb_download_f(lb_lattice *L, void *host_f) { return copy_f(L, host_f, false)
 int lb_init_equilibrium(lb_lattice *L, const void *rho, const void *ux, const void *uy)
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     const long long n = L->cfg.lnx * L->cfg.lny;
     const size_t bytes = (size_t)n * L->elem;
     void *d[3] = {nullptr, nullptr, nullptr};
@@ -486,7 +517,7 @@ int lb_step(lb_lattice *L, int64_t nsteps)
 {
     if (int r = check_ready(L)) return r;
     if (nsteps < 0) return lbm_fail(LB_ERR_INVALID, "nsteps < 0");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     const bool sf = L->cfg.boundary >= LB_SF_COUETTE;
     // Long runs of plain fused steps replay a CUDA graph (one host call per GRAPH_STEPS launches).
     if (L->use_graph && !sf && !L->d_series && nsteps >= 2 * GRAPH_STEPS) {
@@ -525,7 +556,7 @@ int lb_step(lb_lattice *L, int64_t nsteps)
 int lb_stream_only(lb_lattice *L, int64_t nsteps)
 {
     if (int r = check_ready(L)) return r;
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     for (int64_t s = 0; s < nsteps; ++s) {
         int r = L->cfg.dtype == LB_F64 ? launch_step<double>(L, false) : launch_step<float>(L, false);
         if (r) return r;
@@ -649,7 +680,7 @@ int lb_step_host(lb_lattice *L, const void *host_in, void *host_out, int nslabs)
     if (!host_in || !host_out) return lbm_fail(LB_ERR_INVALID, "null host buffer");
     for (int d = 0; d < LB_NUM_DIRS; ++d)
         if (L->nbr[d].base != L->base) return lbm_fail(LB_ERR_STATE, "lb_step_host needs a single self-connected block");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     return L->cfg.dtype == LB_F64 ? step_host_pipelined<double>(L, host_in, host_out, nslabs)
                                   : step_host_pipelined<float>(L, host_in, host_out, nslabs);
 }
@@ -657,7 +688,7 @@ int lb_step_host(lb_lattice *L, const void *host_in, void *host_out, int nslabs)
 int lb_step_timed(lb_lattice *L, int64_t nsteps, float *ms)
 {
     if (!L || !ms) return lbm_fail(LB_ERR_INVALID, "null argument");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     LBM_CUDA(cudaEventRecord(L->ev0, L->stream));
     if (int r = lb_step(L, nsteps)) return r;
     LBM_CUDA(cudaEventRecord(L->ev1, L->stream));
@@ -671,7 +702,7 @@ int64_t lb_steps_done(lb_lattice *L) { return L ? L->steps : -1; }
 int lb_health(lb_lattice *L)
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     LBM_CUDA(cudaStreamSynchronize(L->stream));
     DevState h;
     LBM_CUDA(cudaMemcpy(&h, dev_state(L), sizeof(h), cudaMemcpyDeviceToHost));
@@ -684,7 +715,7 @@ int lb_health(lb_lattice *L)
 int lb_moments(lb_lattice *L, void *rho, void *ux, void *uy)
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     const long long n = L->cfg.lnx * L->cfg.lny;
     const size_t bytes = (size_t)n * L->elem;
     if (!L->d_mom) LBM_CUDA(cudaMalloc(&L->d_mom, 3 * bytes));
@@ -709,7 +740,7 @@ int lb_probe_shear_enable(lb_lattice *L, int64_t l_global, const void *uy_k, int
     if (!L || !uy_k || capacity < 1) return lbm_fail(LB_ERR_INVALID, "bad argument");
     const int64_t l_local = l_global - L->cfg.y0;
     if (l_local < 0 || l_local >= L->cfg.lny) return lbm_fail(LB_ERR_INVALID, "probe row is not inside this block");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     if (L->d_uyk) cudaFree(L->d_uyk);
     if (L->d_series) cudaFree(L->d_series);
     LBM_CUDA(cudaMalloc(&L->d_uyk, (size_t)L->cfg.lnx * L->elem));
@@ -725,7 +756,7 @@ int lb_probe_shear_enable(lb_lattice *L, int64_t l_global, const void *uy_k, int
 int lb_probe_shear_read(lb_lattice *L, void *out, int64_t n)
 {
     if (!L || !out || !L->d_series || n > L->probe_capacity) return lbm_fail(LB_ERR_INVALID, "bad argument");
-    LBM_CUDA(cudaSetDevice(L->cfg.device));
+    LBM_ON_DEVICE(L);
     LBM_CUDA(cudaStreamSynchronize(L->stream));
     LBM_CUDA(cudaMemcpy(out, L->d_series, (size_t)n * L->elem, cudaMemcpyDeviceToHost));
     return 0;
