@@ -238,3 +238,22 @@ def test_graph_replay_equals_single_launches():
     ref = f0.copy()
     orc.cavity_run(ref, 1.7, 64 * 3 + 17)
     assert np.array_equal(outs[0], ref)
+
+
+def test_decomposition_bit_exact_fp32_and_reupload():
+    """fp32 blocks (two-rows-per-iteration interior) and a mid-run download / re-upload cycle."""
+    lb = require_gpu()
+    nx, ny = 67, 530
+    f0 = orc.perturbed_state(nx, ny, np.float32, seed=9)
+    ref = f0.copy()
+    orc.cavity_run(ref, 1.7, 20)
+    for ndx, ndy in ((1, 1), (3, 2)):
+        lat = lb.Lattice(nx, ny, "cavity", omega=1.7, dtype=np.float32, ndx=ndx, ndy=ndy)
+        lat.upload(f0)
+        lat.step(9)
+        mid = lat.download()
+        lat.upload(mid)                      # state round-trips through the host unchanged
+        lat.step(11)
+        assert np.array_equal(lat.download(), ref), (ndx, ndy)
+        lat.health()
+        lat.close()
