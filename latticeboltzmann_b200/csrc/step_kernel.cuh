@@ -246,11 +246,20 @@ __host__ __device__ constexpr int min_ctas_per_sm() { return (sizeof(T) == 8 && 
 
 // Interior cell, split into its load and its compute+store half so that the row loop can be
 // software-pipelined (loads of row k+1 in flight while row k is collided).
+#ifndef LBM_LD_HINT
+#define LBM_LD_HINT 0      // 0: default caching, 1: ld.global.cs (streaming), 2: ld.global.cg (L2 only)
+#endif
+#ifndef LBM_ST_HINT
+#define LBM_ST_HINT 0      // 0: default (write-back), 1: st.global.cs (streaming), 2: st.global.cg
+#endif
 template <typename T>
 __device__ __forceinline__ void interior_load(const StepParams<T> &p, const char *sp, T (&f)[9])
 {
 #pragma unroll
-    for (int i = 0; i < 9; ++i) f[i] = *reinterpret_cast<const T *>(sp + p.ld_off[i]);
+    for (int i = 0; i < 9; ++i) {
+        const T *q = reinterpret_cast<const T *>(sp + p.ld_off[i]);
+        f[i] = LBM_LD_HINT == 1 ? __ldcs(q) : (LBM_LD_HINT == 2 ? __ldcg(q) : *q);
+    }
 }
 template <typename T, int BC, bool EXACT, bool COLLIDE>
 __device__ __forceinline__ void interior_finish(const StepParams<T> &p, T *dp, T (&f)[9])
@@ -263,7 +272,12 @@ __device__ __forceinline__ void interior_finish(const StepParams<T> &p, T *dp, T
     }
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-        *dp = f[i];
+        if (LBM_ST_HINT == 1)
+            __stcs(dp, f[i]);
+        else if (LBM_ST_HINT == 2)
+            __stcg(dp, f[i]);
+        else
+            *dp = f[i];
         dp += p.pop_stride;
     }
 }
