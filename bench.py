@@ -307,8 +307,14 @@ def main():
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
+        from oracle import opt2_numpy
         v, cores, sample = cpu_reference(nx, ny, omega, 3, 1)
-        cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample}
+        cap = int(os.environ.get("LBM_REF_BLOCK", "2048"))
+        one = opt2_numpy.run_independent_blocks(1, cap, cap, omega, 1, 2)
+        cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample,
+               "one_core_value": cap * cap * 2 / one / 1e6,
+               "note": "value: reference-structured opt2 step (np.roll stream + numpy walls + compiled collide) on all cores used; "
+                       "one_core_value: the same on 1 core"}
 
     lat.close()
     if rank == 0:

@@ -75,3 +75,4 @@ def run_independent_blocks(nproc, nx, ny, omega, warmup, steps):
     with ctx.Pool(nproc) as pool:
         res = pool.map(_worker, [(nx, ny, omega, warmup, steps)] * nproc)
     return max(r[0] for r in res)
+
