@@ -8,11 +8,12 @@
 //
 // Scheme: post[i,k,l] = pre[i,k-cx,l-cy] read from buffer
 // `step & 1`, boundary predicates on GLOBAL coordinates, collide in registers,
-// write buffer `(step+1) & 1`.  Every block always owns a one-cell ghost frame;
-// cells on the block's rim additionally store the 3 (faces) / 1 (corners)
-// populations that leave the block straight into the neighbour's ghost frame
-// -- local memory for a self-closed periodic ring, a peer-mapped NVLink address
-// for another GPU.  Interior cells therefore never test for wrap-around.
+// write buffer `(step+1) & 1`.  Every block always owns a one-cell ghost frame
+// (ghost rows inside the arrays, ghost columns in the contiguous `ycol` side
+// arrays, lattice.cuh); cells on the block's rim additionally store the 3 (faces) /
+// 1 (corners) populations that leave the block straight into the neighbour's
+// ghost frame -- local memory for a self-closed periodic ring, a peer-mapped
+// NVLink address for another GPU.  Interior cells never test for wrap-around.
 //
 // Cross-block ordering uses one monotonically increasing flag per direction
 // (DevState::flag_in).  Step n's rim CTAs first wait until all 8 neighbours have
@@ -29,7 +30,6 @@
 namespace lbm {
 
 enum BoundaryKind { BC_PERIODIC = 0, BC_CAVITY = 1, BC_CAVITY_XPERIODIC = 2, BC_SF_COUETTE = 3, BC_SF_POISEUILLE = 4, BC_SF_SLIDING_LID = 5 };
-
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {

@@ -9,12 +9,10 @@ there is NO per-step collective call: the step kernel's rim CTAs store the
 outgoing ghost populations straight into the neighbours' memory over
 NVLink / NVSwitch and order themselves with device-side flags.
 """
-import ctypes
 import os
 
 import numpy as np
 
-from . import _lib
 from ._lib import LbExport
 from .decomposition import Decomposition
 from .lattice import Block
