@@ -103,6 +103,7 @@ typedef struct lb_export {
     int64_t buf_bytes;           /* bytes of one f buffer (there are two, A then B)     */
     int64_t ycol_offset;         /* byte offset of the ghost-column arrays (A then B)   */
     int64_t ycol_bytes;          /* bytes of one ghost-column array                     */
+    int64_t frame_offset;        /* byte offset of the temporal-blocking frame storage  */
     int64_t state_offset;        /* byte offset of the device state block (flags)       */
     int64_t total_bytes;
 } lb_export;
@@ -173,6 +174,10 @@ LB_API int lb_set_rows_per_tile(lb_lattice *lat, int rows);
 /* How long a rim CTA waits for a neighbour's halo flag before the lattice is marked failed
  * (lb_health -> LB_ERR_HALO_TIMEOUT) instead of hanging the GPU.  Default 20 s.            */
 LB_API int lb_set_halo_timeout_ms(lb_lattice *lat, int64_t ms);
+/* Time steps per pass over HBM: 1 = the single-step kernel, 2 = temporal blocking (two steps per
+ * pass, bit-identical results; periodic / cavity boundaries, blocks of at least 16 x 16 cells).
+ * rows_per_tile > 0 overrides the fused tile height (default 64).                               */
+LB_API int lb_set_temporal(lb_lattice *lat, int steps_per_pass, int rows_per_tile);
 /* lb_step replays a CUDA graph of 64 fused steps for long runs (default on).                */
 LB_API int lb_set_use_graph(lb_lattice *lat, int on);
 /* Geometry queries (elements). */

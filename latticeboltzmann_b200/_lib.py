@@ -34,7 +34,7 @@ class LbExport(ctypes.Structure):
     _fields_ = [("ipc_mem_handle", ctypes.c_uint8 * 64), ("local_base", ctypes.c_uint64), ("pid", c_i64),
                 ("device", ctypes.c_int32), ("dtype", ctypes.c_int32), ("lnx", c_i64), ("lny", c_i64),
                 ("pitch", c_i64), ("pop_stride", c_i64), ("buf_bytes", c_i64), ("ycol_offset", c_i64),
-                ("ycol_bytes", c_i64), ("state_offset", c_i64),
+                ("ycol_bytes", c_i64), ("frame_offset", c_i64), ("state_offset", c_i64),
                 ("total_bytes", c_i64)]
 
 
@@ -71,6 +71,7 @@ SYMBOLS = {
     "lb_set_rows_per_tile": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "lb_set_halo_timeout_ms": (ctypes.c_int, [c_vp, c_i64]),
     "lb_set_use_graph": (ctypes.c_int, [c_vp, ctypes.c_int]),
+    "lb_set_temporal": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "lb_pitch": (c_i64, [c_vp]),
     "lb_pop_stride": (c_i64, [c_vp]),
     "lb_kernel_launches": (ctypes.c_int, [c_vp, _P(c_i64)]),

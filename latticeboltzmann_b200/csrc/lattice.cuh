@@ -41,13 +41,48 @@ __host__ __device__ constexpr int dir_opp(int d) { return d == 0 ? 1 : d == 1 ? 
 // Lives at the tail of the block's allocation so that neighbours (other
 // processes / GPUs) can post their "halo pushed" flags straight into it.
 struct DevState {
-    unsigned long long step;               // completed time steps (buffer parity = step & 1)
+    unsigned long long step;               // completed time steps
+    unsigned int cur;                      // which buffer (0 = A, 1 = B) holds the current state; flips once per PASS
+    unsigned int pad0;
     unsigned long long flag_in[NUM_DIRS];  // flag_in[d]: steps whose halos the neighbour in slot d has pushed
     unsigned int edge_done;                // edge CTAs finished in the running launch
     unsigned int all_done;                 // CTAs finished in the running launch
     unsigned int error;                    // != 0: a halo flag wait timed out
-    unsigned int pad;
+    unsigned int frame_done;               // temporal blocking: frame-kernel CTAs finished in the running launch
+    unsigned long long fflag_in[NUM_DIRS]; // temporal blocking: level-(n+1) frame ghosts pushed by the neighbour in slot d
 };
+
+// ---- temporal blocking (two time steps per pass over HBM), temporal.cuh ----------------------------
+// The FRAME of a block = its cells closer than 3 cells to the perimeter.  Its level-(n+1) values live in a
+// small side storage next to the buffers (elements, per block):
+//     top    [9][3][pitch]      rows k = 0..2            element (i,k,l) -> (i*3 + k)*pitch + l + PAD_L
+//     bottom [9][3][pitch]      rows k = lnx-3..lnx-1
+//     left   [9][lnx][4]        columns l = 0..2         element (i,k,l) -> (i*lnx + k)*4 + l
+//     right  [9][lnx][4]        columns l = lny-3..lny-1
+//     grow   [2][3][pitch]      level-(n+1) ghost rows k = -1 (E,NE,SE) and k = lnx (W,NW,SW)
+//     gcol   [2][3][lnx+2]      level-(n+1) ghost columns, same convention as ycol
+constexpr int FRAME_W = 3;
+__host__ __device__ constexpr int xrow_slot(int i) { return (i == 1 || i == 3) ? 0 : ((i == 5 || i == 6) ? 1 : 2); }
+template <typename T>
+struct FrameView {
+    T *top, *bottom, *left, *right, *grow, *gcol;
+};
+__host__ __device__ inline long long frame_elems(long long lnx, long long pitch)
+{
+    return 2 * 27 * pitch + 2 * 36 * lnx + 6 * pitch + 6 * (lnx + 2);
+}
+template <typename T>
+__host__ __device__ inline FrameView<T> frame_view(T *base, long long lnx, long long pitch)
+{
+    FrameView<T> f;
+    f.top = base;
+    f.bottom = f.top + 27 * pitch;
+    f.left = f.bottom + 27 * pitch;
+    f.right = f.left + 36 * lnx;
+    f.grow = f.right + 36 * lnx;
+    f.gcol = f.grow + 6 * pitch;
+    return f;
+}
 
 __host__ __device__ constexpr int ycol_slot(int i) { return (i == 2 || i == 4) ? 0 : ((i == 5 || i == 7) ? 1 : 2); }
 
@@ -56,6 +91,8 @@ struct NbrView {
     T *buf[2];                       // neighbour's buffers A / B (local, peer or IPC-mapped address)
     T *ycol[2];                      // neighbour's ghost-column arrays for buffers A / B
     unsigned long long *flag_in;     // neighbour's DevState::flag_in
+    unsigned long long *fflag_in;    // neighbour's DevState::fflag_in
+    T *frame;                        // neighbour's frame storage (temporal blocking)
     long long pop_stride, pitch;
     int lnx, lny;
 };
@@ -64,6 +101,7 @@ template <typename T>
 struct StepParams {
     T *buf[2];
     T *ycol[2];
+    T *frame;                // frame storage (temporal blocking)
     DevState *st;
     long long pop_stride, pitch;
     long long x0, y0, gnx, gny;
@@ -74,6 +112,7 @@ struct StepParams {
     T omega, u_wall;
     T sf_uw6;                // simple_flows: (1/6)*uw, evaluated in double on the host (PoiseuilleFlow.py:73-74)
     T rho_in, rho_out;       // simple_flows Poiseuille (PoiseuilleFlow.py:134-135)
+    int t2_rows, t2_tiles_l, t2_tiles_k;   // temporal blocking: rows per fused tile, tile grid over the deep interior
     int all_rim;             // 1: every cell takes the general (rim) path, no interior tiles
     int sys_scope;           // 1: some neighbour is on another device / process (system-scope fences)
     unsigned long long halo_timeout_ns;   // give up waiting for a neighbour's flag after this long

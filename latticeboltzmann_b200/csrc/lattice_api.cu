@@ -13,6 +13,7 @@
 #include "../../include/lbm_b200.h"
 #include "api_common.h"
 #include "step_kernel.cuh"
+#include "temporal.cuh"
 
 using namespace lbm;
 
@@ -26,7 +27,7 @@ struct lb_lattice {
     lb_config cfg{};
     size_t elem = 8;
     char *base = nullptr;
-    size_t buf_bytes = 0, ycol_off = 0, ycol_bytes = 0, state_off = 0, total_bytes = 0;
+    size_t buf_bytes = 0, ycol_off = 0, ycol_bytes = 0, frame_off = 0, state_off = 0, total_bytes = 0;
     long long pitch = 0, pop_stride = 0;
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -39,7 +40,10 @@ struct lb_lattice {
     cudaStream_t graph_stream = nullptr;
     int graph_rows_per_tile = 0;
     bool use_graph = true;
+    int temporal = 1;            // time steps per pass over HBM: 1 (single-step kernel) or 2 (temporal.cuh)
+    int t2_rows = 64;
     int64_t steps = 0;
+    int cur = 0;                 // host mirror of DevState::cur (buffer holding the current state)
     int64_t launches = 0;
     // shear probe
     void *d_uyk = nullptr, *d_series = nullptr;
@@ -92,6 +96,7 @@ StepParams<T> make_params(lb_lattice *L)
     p.buf[1] = reinterpret_cast<T *>(L->base + L->buf_bytes);
     p.ycol[0] = reinterpret_cast<T *>(L->base + L->ycol_off);
     p.ycol[1] = reinterpret_cast<T *>(L->base + L->ycol_off + L->ycol_bytes);
+    p.frame = reinterpret_cast<T *>(L->base + L->frame_off);
     p.st = dev_state(L);
     p.pop_stride = L->pop_stride;
     p.pitch = L->pitch;
@@ -114,6 +119,9 @@ StepParams<T> make_params(lb_lattice *L)
         p.n_perimeter = (long long)p.lny + (p.lnx > 1 ? p.lny : 0) + (p.lny > 1 ? 2 : 1) * (long long)(p.lnx > 2 ? p.lnx - 2 : 0);
     }
     p.n_rim_ctas = (int)((p.n_perimeter + TILE_L - 1) / TILE_L);
+    p.t2_rows = L->t2_rows;
+    p.t2_tiles_l = p.lny > 4 ? (p.lny - 4 + T2_W - 1) / T2_W : 0;
+    p.t2_tiles_k = p.lnx > 4 ? (p.lnx - 4 + p.t2_rows - 1) / p.t2_rows : 0;
     p.sf_uw6 = (T)((1.0 / 6.0) * L->cfg.u_wall);
     p.rho_in = (T)L->cfg.rho_in;
     p.rho_out = (T)L->cfg.rho_out;
@@ -133,6 +141,8 @@ StepParams<T> make_params(lb_lattice *L)
         p.nbr[d].ycol[0] = reinterpret_cast<T *>(n.base + n.exp.ycol_offset);
         p.nbr[d].ycol[1] = reinterpret_cast<T *>(n.base + n.exp.ycol_offset + n.exp.ycol_bytes);
         p.nbr[d].flag_in = reinterpret_cast<DevState *>(n.base + n.exp.state_offset)->flag_in;
+        p.nbr[d].fflag_in = reinterpret_cast<DevState *>(n.base + n.exp.state_offset)->fflag_in;
+        p.nbr[d].frame = reinterpret_cast<T *>(n.base + n.exp.frame_offset);
         p.nbr[d].pop_stride = n.exp.pop_stride;
         p.nbr[d].pitch = n.exp.pitch;
         p.nbr[d].lnx = (int)n.exp.lnx;
@@ -174,6 +184,46 @@ int launch_step(lb_lattice *L, bool collide)
     default:
         return lbm_fail(LB_ERR_INVALID, "unknown boundary mode %d", L->cfg.boundary);
     }
+}
+
+// One double step (temporal.cuh): frame level n+1, fused deep interior, frame level n+2.
+template <typename T, int BC, bool EXACT>
+int launch_double_bc(lb_lattice *L, const StepParams<T> &p)
+{
+    static bool attr_set[64] = {};           // per device: the fused tile's shared-memory ring exceeds the 48 KB default
+    const int dev = L->cfg.device & 63;
+    if (!attr_set[dev]) {
+        LBM_CUDA(cudaFuncSetAttribute(t2_interior_kernel<T, BC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2_smem_bytes<T>()));
+        attr_set[dev] = true;
+    }
+    const int g1 = (int)((ring_cells(p.lnx, p.lny, FRAME_W) + TILE_L - 1) / TILE_L);
+    const int g3 = (int)((ring_cells(p.lnx, p.lny, 2) + TILE_L - 1) / TILE_L);
+    t2_frame1_kernel<T, BC, EXACT><<<g1, TILE_L, 0, L->stream>>>(p);
+    t2_interior_kernel<T, BC, EXACT><<<p.t2_tiles_l * p.t2_tiles_k, TILE_L, t2_smem_bytes<T>(), L->stream>>>(p);
+    t2_frame2_kernel<T, BC, EXACT><<<g3, TILE_L, 0, L->stream>>>(p);
+    return 0;
+}
+
+template <typename T>
+int launch_double(lb_lattice *L)
+{
+    const StepParams<T> p = make_params<T>(L);
+    const bool exact = L->cfg.arith == LB_ARITH_EXACT;
+    switch (L->cfg.boundary) {
+    case LB_PERIODIC:
+        return exact ? launch_double_bc<T, BC_PERIODIC, true>(L, p) : launch_double_bc<T, BC_PERIODIC, false>(L, p);
+    case LB_CAVITY:
+        return exact ? launch_double_bc<T, BC_CAVITY, true>(L, p) : launch_double_bc<T, BC_CAVITY, false>(L, p);
+    case LB_CAVITY_XPERIODIC:
+        return exact ? launch_double_bc<T, BC_CAVITY_XPERIODIC, true>(L, p) : launch_double_bc<T, BC_CAVITY_XPERIODIC, false>(L, p);
+    default:
+        return lbm_fail(LB_ERR_INVALID, "temporal blocking supports the periodic and cavity boundaries");
+    }
+}
+
+bool temporal_ok(const lb_lattice *L)
+{
+    return L->temporal == 2 && L->cfg.boundary <= LB_CAVITY_XPERIODIC && L->cfg.lnx >= 16 && L->cfg.lny >= 16 && !L->d_series;
 }
 
 // simple_flows step orders.  The pre-kernels rewrite the current buffer in
@@ -259,7 +309,9 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     L->buf_bytes = (L->buf_bytes + 255) / 256 * 256;
     L->ycol_off = 2 * L->buf_bytes;
     L->ycol_bytes = ((size_t)6 * (cfg->lnx + 2) * L->elem + 255) / 256 * 256;   // one ghost-column array per buffer
-    L->state_off = L->ycol_off + 2 * L->ycol_bytes;
+    L->frame_off = L->ycol_off + 2 * L->ycol_bytes;
+    const size_t frame_bytes = ((size_t)frame_elems(cfg->lnx, L->pitch) * L->elem + 255) / 256 * 256;
+    L->state_off = L->frame_off + frame_bytes;
     L->total_bytes = L->state_off + 256;
     cudaError_t e = cudaMalloc(&L->base, L->total_bytes);
     if (e != cudaSuccess) {
@@ -281,6 +333,8 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
         return lbm_fail(LB_ERR_CUDA, "lattice set-up failed: %s", cudaGetErrorString(e));
     }
     L->rows_per_tile = cfg->dtype == LB_F64 ? 4 : 8;     // measured optima
+    if (const char *t = getenv("LBM_TEMPORAL")) L->temporal = atoi(t) == 2 ? 2 : 1;
+    if (const char *t = getenv("LBM_T2_ROWS")) if (atoi(t) > 0) L->t2_rows = atoi(t);
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
     *out = L;
@@ -336,6 +390,14 @@ int lb_set_halo_timeout_ms(lb_lattice *L, int64_t ms)
     return 0;
 }
 
+int lb_set_temporal(lb_lattice *L, int steps_per_pass, int rows_per_tile)
+{
+    if (!L || (steps_per_pass != 1 && steps_per_pass != 2)) return lbm_fail(LB_ERR_INVALID, "steps_per_pass must be 1 or 2");
+    L->temporal = steps_per_pass;
+    if (rows_per_tile > 0) L->t2_rows = rows_per_tile;
+    return 0;
+}
+
 int lb_set_use_graph(lb_lattice *L, int on)
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
@@ -374,6 +436,7 @@ int lb_get_export(lb_lattice *L, lb_export *out)
     out->buf_bytes = (int64_t)L->buf_bytes;
     out->ycol_offset = (int64_t)L->ycol_off;
     out->ycol_bytes = (int64_t)L->ycol_bytes;
+    out->frame_offset = (int64_t)L->frame_off;
     out->state_offset = (int64_t)L->state_off;
     out->total_bytes = (int64_t)L->total_bytes;
     return 0;
@@ -440,7 +503,7 @@ static int copy_f(lb_lattice *L, void *host, bool upload)
     if (!L || !host) return lbm_fail(LB_ERR_INVALID, "null argument");
     LBM_ON_DEVICE(L);
     const size_t e = L->elem;
-    char *cur = L->base + (L->steps & 1) * L->buf_bytes;
+    char *cur = L->base + (size_t)L->cur * L->buf_bytes;
     const size_t row = (size_t)L->cfg.lny * e;
     for (int i = 0; i < 9; ++i) {
         char *d = cur + ((size_t)i * L->pop_stride + (size_t)L->pitch + PAD_L) * e;
@@ -519,13 +582,25 @@ int lb_step(lb_lattice *L, int64_t nsteps)
     if (nsteps < 0) return lbm_fail(LB_ERR_INVALID, "nsteps < 0");
     LBM_ON_DEVICE(L);
     const bool sf = L->cfg.boundary >= LB_SF_COUETTE;
+    // Temporal blocking: two steps per pass over HBM (three launches per double step).
+    if (temporal_ok(L)) {
+        while (nsteps >= 2) {
+            int r = L->cfg.dtype == LB_F64 ? launch_double<double>(L) : launch_double<float>(L);
+            if (r) return r;
+            L->launches += 3;
+            L->steps += 2;
+            L->cur ^= 1;
+            nsteps -= 2;
+        }
+        LBM_CUDA(cudaGetLastError());
+    }
     // Long runs of plain fused steps replay a CUDA graph (one host call per GRAPH_STEPS launches).
     if (L->use_graph && !sf && !L->d_series && nsteps >= 2 * GRAPH_STEPS) {
         if (int r = ensure_graph(L)) return r;
         while (nsteps >= GRAPH_STEPS) {
             LBM_CUDA(cudaGraphLaunch(L->graph_exec, L->stream));
             L->launches += GRAPH_STEPS;
-            L->steps += GRAPH_STEPS;
+            L->steps += GRAPH_STEPS;          // an even number of buffer flips
             nsteps -= GRAPH_STEPS;
         }
     }
@@ -537,6 +612,7 @@ int lb_step(lb_lattice *L, int64_t nsteps)
         if (r) return r;
         L->launches++;
         L->steps++;
+        L->cur ^= 1;
         if (L->d_series) {
             if (L->cfg.dtype == LB_F64)
                 shear_probe_kernel<double><<<1, 256, 0, L->stream>>>(make_params<double>(L), (int)L->probe_l_local, (const double *)L->d_uyk,
@@ -562,6 +638,7 @@ int lb_stream_only(lb_lattice *L, int64_t nsteps)
         if (r) return r;
         L->launches++;
         L->steps++;
+        L->cur ^= 1;
     }
     LBM_CUDA(cudaGetLastError());
     return 0;
@@ -626,7 +703,7 @@ int step_host_pipelined(lb_lattice *L, const void *host_in, void *host_out, int 
         L->ev_done.push_back(b);
     }
     const StepParams<T> p = make_params<T>(L);
-    const int par = (int)(L->steps & 1);
+    const int par = L->cur;
     void *hin = const_cast<void *>(host_in);
     auto lo = [&](int j) { return lnx * j / nslabs; };
     // everything already queued on the lattice's stream (previous steps) must precede the uploads
@@ -659,6 +736,7 @@ int step_host_pipelined(lb_lattice *L, const void *host_in, void *host_out, int 
     advance_step_kernel<<<1, 1, 0, L->stream>>>(dev_state(L));
     L->launches += 2;
     L->steps++;
+    L->cur ^= 1;
     LBM_CUDA(cudaGetLastError());
     LBM_CUDA(cudaEventRecord(L->ev_fin, L->s_d2h));
     LBM_CUDA(cudaStreamWaitEvent(L->stream, L->ev_fin, 0));

@@ -7,8 +7,8 @@
 //   D2Q9.collide()           c/d2q9.h:121-131        (serial C++ loop)
 //
 // Scheme: post[i,k,l] = pre[i,k-cx,l-cy] read from buffer
-// `step & 1`, boundary predicates on GLOBAL coordinates, collide in registers,
-// write buffer `(step+1) & 1`.  Every block always owns a one-cell ghost frame
+// `cur`, boundary predicates on GLOBAL coordinates, collide in registers,
+// write the other buffer.  Every block always owns a one-cell ghost frame
 // (ghost rows inside the arrays, ghost columns in the contiguous `ycol` side
 // arrays, lattice.cuh); cells on the block's rim additionally store the 3 (faces) /
 // 1 (corners) populations that leave the block straight into the neighbour's
@@ -322,12 +322,13 @@ __device__ __forceinline__ void rim_cta(const StepParams<T> &p, DevState *st, un
 
 // The last CTA of the launch publishes the new step count (read by the next launch -- which makes
 // the launch arguments step-independent and the whole loop CUDA-graph replayable).
-__device__ __forceinline__ void publish_step(DevState *st, unsigned long long step)
+__device__ __forceinline__ void publish_step(DevState *st, unsigned long long step, int par)
 {
     if (threadIdx.x == 0) {
         const unsigned int prev = atomicAdd(&st->all_done, 1u);
         if (prev == gridDim.x - 1u) {
             st->all_done = 0u;
+            *(volatile unsigned int *)&st->cur = (unsigned int)(par ^ 1);
             *(volatile unsigned long long *)&st->step = step + 1ull;
         }
     }
@@ -338,7 +339,7 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
 {
     DevState *st = p.st;
     const unsigned long long step = *(volatile unsigned long long *)&st->step;
-    const int par = (int)(step & 1ull);
+    const int par = (int)*(volatile unsigned int *)&st->cur;
     const T *__restrict__ src = p.buf[par];
     T *__restrict__ dst = p.buf[par ^ 1];
 
@@ -383,7 +384,7 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
         }
         __syncthreads();
     }
-    publish_step(st, step);
+    publish_step(st, step, par);
 }
 
 // Rows [k_lo, k_hi) of one step through the general (rim) cell path, without the flag protocol and
@@ -392,7 +393,7 @@ __global__ void __launch_bounds__(TILE_L, min_ctas_per_sm<T, EXACT>()) step_kern
 template <typename T, int BC, bool EXACT>
 __global__ void __launch_bounds__(TILE_L) step_rows_kernel(const __grid_constant__ StepParams<T> p, int k_lo, int k_hi)
 {
-    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
     const T *__restrict__ src = p.buf[par];
     T *__restrict__ dst = p.buf[par ^ 1];
     const int tiles_l = (p.lny + TILE_L - 1) / TILE_L;
@@ -407,6 +408,7 @@ __global__ void advance_step_kernel(DevState *st)
 {
     const unsigned long long s = st->step + 1ull;
     st->step = s;
+    st->cur ^= 1u;
     for (int d = 0; d < NUM_DIRS; ++d) st->flag_in[d] = s;
 }
 
@@ -414,7 +416,7 @@ __global__ void advance_step_kernel(DevState *st)
 template <typename T>
 __global__ void halo_refresh_kernel(const __grid_constant__ StepParams<T> p, int k_lo, int k_hi)
 {
-    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
     const T *src = p.buf[par];
     const long long n_rim = 2ll * p.lnx + 2ll * p.lny;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n_rim; t += (long long)gridDim.x * blockDim.x) {
@@ -436,7 +438,7 @@ template <typename T>
 __global__ void init_equilibrium_kernel(const __grid_constant__ StepParams<T> p, const T *__restrict__ rho,
                                         const T *__restrict__ ux, const T *__restrict__ uy)
 {
-    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
     T *dst = p.buf[par];
     const long long n = (long long)p.lnx * p.lny;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -453,7 +455,7 @@ template <typename T, bool SF>
 __global__ void moments_kernel(const __grid_constant__ StepParams<T> p, T *__restrict__ rho, T *__restrict__ ux,
                                T *__restrict__ uy)
 {
-    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
     const T *src = p.buf[par];
     const long long n = (long long)p.lnx * p.lny;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -477,7 +479,7 @@ __global__ void moments_kernel(const __grid_constant__ StepParams<T> p, T *__res
 template <typename T>
 __global__ void sf_collide_inplace_kernel(const __grid_constant__ StepParams<T> p)
 {
-    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
     T *buf = p.buf[par];
     const long long n = (long long)p.lnx * p.lny;
     for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
@@ -498,7 +500,7 @@ __global__ void sf_collide_inplace_kernel(const __grid_constant__ StepParams<T> 
 template <typename T>
 __global__ void sf_pressure_kernel(const __grid_constant__ StepParams<T> p)
 {
-    const int par = (int)(*(volatile unsigned long long *)&p.st->step & 1ull);
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
     T *buf = p.buf[par];
     const int X = p.lnx - 1;
     for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < p.lny; l += gridDim.x * blockDim.x) {
@@ -526,7 +528,7 @@ __global__ void shear_probe_kernel(const __grid_constant__ StepParams<T> p, int 
 {
     __shared__ T red[256];
     const unsigned long long step = *(volatile unsigned long long *)&p.st->step;
-    const int par = (int)(step & 1ull);
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
     const T *src = p.buf[par];
     T acc = T(0);
     for (int k = threadIdx.x; k < p.lnx; k += blockDim.x) {

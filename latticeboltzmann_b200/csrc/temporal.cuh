@@ -1,0 +1,326 @@
+// Temporal blocking: TWO time steps per pass over HBM ("double step").
+//
+// The single-step kernel is at the DRAM pins (144 B per cell per step, step_kernel.cuh).  The only way
+// past that roofline is to touch HBM less: advance a tile two levels while it sits on chip, so that a
+// cell costs 72 B read + 72 B written per TWO steps.  Results are bit-identical to two single steps
+// (same per-level arithmetic, same boundary rules, same halo values).
+//
+// One double step n -> n+2 of a block is three launches on the block's stream:
+//
+//   K1  t2_frame1   level n -> n+1 on the FRAME (cells closer than 3 to the block perimeter), from the
+//                   main buffer and its level-n ghosts, into the small frame storage (lattice.cuh);
+//                   perimeter cells push their leaving populations into the neighbours' level-(n+1)
+//                   frame ghosts (peer stores) and the last CTA posts fflag = n+1.
+//   K2  t2_interior level n -> n+2 on the DEEP INTERIOR (distance >= 2): per tile, rows of level n+1
+//                   (one-cell halo, recomputed redundantly at tile edges: 2 rows per t2_rows, 2 columns
+//                   per 254) go through a 4-row shared-memory ring and are consumed by the level-(n+2)
+//                   pull.  No ghosts, no walls, no flags: all sources are real cells of this block.
+//   K3  t2_frame2   level n+1 -> n+2 on the cells closer than 2 to the perimeter, from the frame storage
+//                   and the level-(n+1) frame ghosts; stores into the main destination buffer, pushes the
+//                   level-(n+2) halos into the neighbours' main ghosts (push_halo), posts flag = n+2 and
+//                   publishes step = n+2.
+//
+// Flag protocol (monotone counters in DevState, same reasoning as step_kernel.cuh): K1 waits for
+// flag_in >= n (level-n main ghosts present, neighbours done with the frame ghosts K1 overwrites), K3
+// waits for fflag_in >= n+1 (level-(n+1) frame ghosts present).  K2 runs between them on the same
+// stream and gives the exchange a whole interior update of slack.
+#pragma once
+#include "step_kernel.cuh"
+
+namespace lbm {
+
+constexpr int T2_W = TILE_L - 2;      // output columns per fused tile (256 level-(n+1) columns incl. halo)
+constexpr int T2_SLOTS = 4;           // shared-memory ring of level-(n+1) rows
+
+template <typename T>
+__host__ __device__ constexpr int t2_smem_bytes() { return T2_SLOTS * 9 * TILE_L * (int)sizeof(T); }
+
+// cells closer than w to the perimeter (needs lnx, lny >= 2w)
+__host__ __device__ inline long long ring_cells(int lnx, int lny, int w) { return 2ll * w * lny + 2ll * w * (lnx - 2 * w); }
+
+__device__ __forceinline__ void decode_ring(int lnx, int lny, int w, long long t, int &k, int &l)
+{
+    const long long a = (long long)w * lny;
+    if (t < a) { k = (int)(t / lny); l = (int)(t - (long long)k * lny); return; }
+    t -= a;
+    if (t < a) { const int r = (int)(t / lny); k = lnx - w + r; l = (int)(t - (long long)r * lny); return; }
+    t -= a;
+    const int m = lnx - 2 * w;
+    const long long c = (long long)w * m;
+    if (t < c) { l = (int)(t / m); k = w + (int)(t - (long long)l * m); return; }
+    t -= c;
+    const int r = (int)(t / m);
+    l = lny - w + r;
+    k = w + (int)(t - (long long)r * m);
+}
+
+template <typename T>
+__device__ __forceinline__ T *frame_ptr(const FrameView<T> &f, int lnx, int lny, long long pitch, int i, int k, int l)
+{
+    if (k < FRAME_W) return f.top + ((long long)i * 3 + k) * pitch + (l + PAD_L);
+    if (k >= lnx - FRAME_W) return f.bottom + ((long long)i * 3 + (k - (lnx - FRAME_W))) * pitch + (l + PAD_L);
+    if (l < FRAME_W) return f.left + ((long long)i * lnx + k) * 4 + l;
+    return f.right + ((long long)i * lnx + k) * 4 + (l - (lny - FRAME_W));
+}
+
+// ---- sources of a general (boundary-aware) cell update ------------------------------------------------
+// level n: the main buffer with its ghost rows and ycol ghost columns (what update_cell<RIM> reads)
+template <typename T>
+struct SrcMain {
+    const StepParams<T> &p;
+    const T *src;
+    const T *ycol;
+    int k, l;
+    template <int I>
+    __device__ __forceinline__ T pull() const
+    {
+        if (cy_of(I) == 1 && l == 0) return __ldcg(ycol + (0 * 3 + ycol_slot(I)) * (long long)(p.lnx + 2) + (k - cx_of(I) + 1));
+        if (cy_of(I) == -1 && l == p.lny - 1) return __ldcg(ycol + (1 * 3 + ycol_slot(I)) * (long long)(p.lnx + 2) + (k - cx_of(I) + 1));
+        return __ldcg(src + (long long)I * p.pop_stride + (long long)(k - cx_of(I) + 1) * p.pitch + (l - cy_of(I) + PAD_L));
+    }
+    __device__ __forceinline__ T own(int i) const { return __ldcg(src + (long long)i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L)); }
+};
+
+// level n+1: the frame storage and the level-(n+1) frame ghosts
+template <typename T>
+struct SrcFrame {
+    const StepParams<T> &p;
+    FrameView<T> fv;
+    int k, l;
+    template <int I>
+    __device__ __forceinline__ T pull() const
+    {
+        const int kk = k - cx_of(I), ll = l - cy_of(I);
+        if (ll < 0) return __ldcg(fv.gcol + (0 * 3 + ycol_slot(I)) * (long long)(p.lnx + 2) + (kk + 1));
+        if (ll >= p.lny) return __ldcg(fv.gcol + (1 * 3 + ycol_slot(I)) * (long long)(p.lnx + 2) + (kk + 1));
+        if (kk < 0) return __ldcg(fv.grow + (0 * 3 + xrow_slot(I)) * p.pitch + (ll + PAD_L));
+        if (kk >= p.lnx) return __ldcg(fv.grow + (1 * 3 + xrow_slot(I)) * p.pitch + (ll + PAD_L));
+        return __ldcg(frame_ptr<T>(fv, p.lnx, p.lny, p.pitch, I, kk, ll));
+    }
+    __device__ __forceinline__ T own(int i) const { return __ldcg(frame_ptr<T>(fv, p.lnx, p.lny, p.pitch, i, k, l)); }
+};
+
+template <typename T, typename Src>
+__device__ __forceinline__ void pull9(const Src &s, T (&f)[9])
+{
+    f[0] = s.template pull<0>();
+    f[1] = s.template pull<1>();
+    f[2] = s.template pull<2>();
+    f[3] = s.template pull<3>();
+    f[4] = s.template pull<4>();
+    f[5] = s.template pull<5>();
+    f[6] = s.template pull<6>();
+    f[7] = s.template pull<7>();
+    f[8] = s.template pull<8>();
+}
+
+// The wall / lid rules of update_cell (cavity_opt2.py:133-177 as a gather) on top of a generic source.
+template <typename T, int BC, typename Src>
+__device__ __forceinline__ void wall_rules(const StepParams<T> &p, const Src &s, T (&f)[9], int k, int l)
+{
+    if (BC == BC_PERIODIC) return;
+    const long long gk = p.x0 + k, gl = p.y0 + l;
+    const bool walls = (BC == BC_CAVITY);
+    const bool bottom = (gl == 0), top = (gl == p.gny - 1);
+    const bool left = walls && (gk == 0), right = walls && (gk == p.gnx - 1);
+    if (!(bottom | top | left | right)) return;
+    T lid = T(0), o_nw = T(0), o_ne = T(0);
+    if (top) {
+        o_nw = s.own(QNW);
+        o_ne = s.own(QNE);
+        T rho = rn_add(o_nw, s.own(QN));
+        rho = rn_add(rho, o_ne);
+        rho = rn_add(rho, f[QNW]);
+        rho = rn_add(rho, f[QN]);
+        rho = rn_add(rho, f[QNE]);
+        rho = rn_add(rho, f[QW]);
+        rho = rn_add(rho, f[Q0]);
+        rho = rn_add(rho, f[QE]);
+        const T six_w = rn_mul(T(6), T(1.0 / 36.0));
+        lid = rn_mul(rn_mul(six_w, rho), p.u_wall);
+    }
+#pragma unroll
+    for (int i = 1; i < 9; ++i) {
+        const bool outside = (cy_of(i) == 1 && bottom) || (cy_of(i) == -1 && top) || (cx_of(i) == 1 && left) || (cx_of(i) == -1 && right);
+        if (outside) f[i] = s.own(opp_of(i));
+    }
+    if (top) {
+        if (!left) f[QSE] = rn_add(o_nw, lid);
+        if (!right) f[QSW] = rn_sub(o_ne, lid);
+    }
+}
+
+// Perimeter cell (k, l): store the level-(n+1) populations that leave the block into the neighbours'
+// level-(n+1) frame ghosts (mirror of push_halo).
+template <typename T>
+__device__ __forceinline__ void push_frame_halo(const StepParams<T> &p, int k, int l, const T (&f)[9])
+{
+    const bool xl = (k == 0), xh = (k == p.lnx - 1), yl = (l == 0), yh = (l == p.lny - 1);
+    if (!(xl | xh | yl | yh)) return;
+#define LBM_FPUSH_X(D, SIDE, LL, I)                                                              \
+    do {                                                                                         \
+        const NbrView<T> &nb = p.nbr[D];                                                         \
+        const FrameView<T> nf = frame_view<T>(nb.frame, nb.lnx, nb.pitch);                       \
+        nf.grow[((SIDE) * 3 + xrow_slot(I)) * nb.pitch + ((LL) + PAD_L)] = f[I];                 \
+    } while (0)
+#define LBM_FPUSH_Y(D, SIDE, KK, I)                                                              \
+    do {                                                                                         \
+        const NbrView<T> &nb = p.nbr[D];                                                         \
+        const FrameView<T> nf = frame_view<T>(nb.frame, nb.lnx, nb.pitch);                       \
+        nf.gcol[((SIDE) * 3 + ycol_slot(I)) * (long long)(nb.lnx + 2) + ((KK) + 1)] = f[I];      \
+    } while (0)
+    if (xh) { LBM_FPUSH_X(1, 0, l, QE); LBM_FPUSH_X(1, 0, l, QNE); LBM_FPUSH_X(1, 0, l, QSE); }   // -> ghost row -1 of the right neighbour
+    if (xl) { LBM_FPUSH_X(0, 1, l, QW); LBM_FPUSH_X(0, 1, l, QNW); LBM_FPUSH_X(0, 1, l, QSW); }   // -> ghost row lnx of the left neighbour
+    if (yh) { LBM_FPUSH_Y(3, 0, k, QN); LBM_FPUSH_Y(3, 0, k, QNE); LBM_FPUSH_Y(3, 0, k, QNW); }
+    if (yl) { LBM_FPUSH_Y(2, 1, k, QS); LBM_FPUSH_Y(2, 1, k, QSW); LBM_FPUSH_Y(2, 1, k, QSE); }
+    if (xh && yh) LBM_FPUSH_Y(7, 0, -1, QNE);
+    if (xh && yl) LBM_FPUSH_Y(6, 1, -1, QSE);
+    if (xl && yh) LBM_FPUSH_Y(5, 0, p.nbr[5].lnx, QNW);
+    if (xl && yl) LBM_FPUSH_Y(4, 1, p.nbr[4].lnx, QSW);
+#undef LBM_FPUSH_X
+#undef LBM_FPUSH_Y
+}
+
+__device__ __forceinline__ void wait_flags(const unsigned long long *flags, unsigned long long want, DevState *st, unsigned long long timeout_ns)
+{
+    if (threadIdx.x < NUM_DIRS) {
+        if (ld_acquire_sys(&flags[threadIdx.x]) < want && *(volatile unsigned int *)&st->error == 0) {
+            const unsigned long long t0 = global_timer_ns();
+            while (ld_acquire_sys(&flags[threadIdx.x]) < want) {
+                if (global_timer_ns() - t0 > timeout_ns) {
+                    atomicExch(&st->error, 1u);
+                    break;
+                }
+            }
+        }
+    }
+    __syncthreads();
+}
+
+// K1: level n -> n+1 on the frame.
+template <typename T, int BC, bool EXACT>
+__global__ void __launch_bounds__(TILE_L) t2_frame1_kernel(const __grid_constant__ StepParams<T> p)
+{
+    DevState *st = p.st;
+    const unsigned long long step = *(volatile unsigned long long *)&st->step;
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
+    wait_flags(st->flag_in, step, st, p.halo_timeout_ns);
+    const long long t = (long long)blockIdx.x * TILE_L + threadIdx.x;
+    if (t < ring_cells(p.lnx, p.lny, FRAME_W)) {
+        int k, l;
+        decode_ring(p.lnx, p.lny, FRAME_W, t, k, l);
+        const SrcMain<T> s{p, p.buf[par], p.ycol[par], k, l};
+        T f[9];
+        pull9<T>(s, f);
+        wall_rules<T, BC>(p, s, f, k, l);
+        d2q9_collide<T, EXACT>(f, p.omega);
+        const FrameView<T> fv = frame_view<T>(p.frame, p.lnx, p.pitch);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) *frame_ptr<T>(fv, p.lnx, p.lny, p.pitch, i, k, l) = f[i];
+        push_frame_halo<T>(p, k, l, f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        halo_fence(p.sys_scope);
+        const unsigned int prev = atomicAdd(&st->frame_done, 1u);
+        if (prev == gridDim.x - 1u) {
+            st->frame_done = 0u;
+            halo_fence(p.sys_scope);
+#pragma unroll
+            for (int d = 0; d < NUM_DIRS; ++d) st_relaxed_sys(p.nbr[d].fflag_in + dir_opp(d), step + 1ull);
+        }
+    }
+}
+
+// K3: level n+1 -> n+2 on the cells closer than 2 to the perimeter; completes the double step.
+template <typename T, int BC, bool EXACT>
+__global__ void __launch_bounds__(TILE_L) t2_frame2_kernel(const __grid_constant__ StepParams<T> p)
+{
+    DevState *st = p.st;
+    const unsigned long long step = *(volatile unsigned long long *)&st->step;
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
+    T *__restrict__ dst = p.buf[par ^ 1];
+    wait_flags(st->fflag_in, step + 1ull, st, p.halo_timeout_ns);
+    const long long t = (long long)blockIdx.x * TILE_L + threadIdx.x;
+    if (t < ring_cells(p.lnx, p.lny, 2)) {
+        int k, l;
+        decode_ring(p.lnx, p.lny, 2, t, k, l);
+        const SrcFrame<T> s{p, frame_view<T>(p.frame, p.lnx, p.pitch), k, l};
+        T f[9];
+        pull9<T>(s, f);
+        wall_rules<T, BC>(p, s, f, k, l);
+        d2q9_collide<T, EXACT>(f, p.omega);
+        T *dp = dst + (long long)(k + 1) * p.pitch + (l + PAD_L);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) dp[(long long)i * p.pop_stride] = f[i];
+        push_halo<T>(p, par ^ 1, k, l, f);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        halo_fence(p.sys_scope);
+        const unsigned int prev = atomicAdd(&st->frame_done, 1u);
+        if (prev == gridDim.x - 1u) {
+            st->frame_done = 0u;
+            halo_fence(p.sys_scope);
+#pragma unroll
+            for (int d = 0; d < NUM_DIRS; ++d) st_relaxed_sys(p.nbr[d].flag_in + dir_opp(d), step + 2ull);
+            *(volatile unsigned int *)&st->cur = (unsigned int)(par ^ 1);  // ONE buffer flip per pass, two steps
+            *(volatile unsigned long long *)&st->step = step + 2ull;     // K1 and K2 of this double step are complete (stream order)
+        }
+    }
+}
+
+// K2: level n -> n+2 on the deep interior through a shared-memory ring of level-(n+1) rows.
+template <typename T, int BC, bool EXACT>
+__global__ void __launch_bounds__(TILE_L) t2_interior_kernel(const __grid_constant__ StepParams<T> p)
+{
+    extern __shared__ __align__(16) unsigned char t2_smem_raw[];
+    T *ring = reinterpret_cast<T *>(t2_smem_raw);               // [T2_SLOTS][9][TILE_L]
+    const unsigned long long step = *(volatile unsigned long long *)&p.st->step;
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
+    const T *__restrict__ src = p.buf[par];
+    T *__restrict__ dst = p.buf[par ^ 1];
+
+    const int kt = (int)blockIdx.x / p.t2_tiles_l, lt = (int)blockIdx.x - kt * p.t2_tiles_l;
+    const int k0 = 2 + kt * p.t2_rows;
+    const int k1 = min(k0 + p.t2_rows, p.lnx - 2);
+    const int t = threadIdx.x;
+    const int lc = 2 + lt * T2_W - 1 + t;                       // this thread's column (level n+1 and level n+2)
+    const bool have1 = lc <= p.lny - 2;                         // a level-(n+1) cell at distance >= 1
+    const bool have2 = t >= 1 && t <= T2_W && lc <= p.lny - 3;  // a level-(n+2) cell at distance >= 2
+    const long long row_bytes = p.pitch * (long long)sizeof(T);
+    const char *sp = reinterpret_cast<const char *>(src + (long long)k0 * p.pitch + (lc + PAD_L));        // row k0-1
+    T *dp = dst + (long long)(k0 + 1) * p.pitch + (lc + PAD_L);                                           // row k0
+#pragma unroll 1
+    for (int j = k0 - 1; j <= k1; ++j) {
+        if (have1) {
+            T f[9];
+            interior_load<T>(p, sp, f);
+            d2q9_collide<T, EXACT>(f, p.omega);
+            T *slot = ring + (long long)(j & (T2_SLOTS - 1)) * 9 * TILE_L + t;
+#pragma unroll
+            for (int i = 0; i < 9; ++i) slot[i * TILE_L] = f[i];
+        }
+        sp += row_bytes;
+        __syncthreads();
+        if (j >= k0 + 1) {                                       // level-(n+1) rows j-2, j-1, j are in the ring: emit row j-1
+            if (have2) {
+                const int jo = j - 1;
+                T f[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i)
+                    f[i] = ring[((long long)((jo - cx_of(i)) & (T2_SLOTS - 1)) * 9 + i) * TILE_L + (t - cy_of(i))];
+                d2q9_collide<T, EXACT>(f, p.omega);
+                T *q = dp;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) {
+                    *q = f[i];
+                    q += p.pop_stride;
+                }
+            }
+            dp += p.pitch;
+        }
+    }
+}
+
+}  // namespace lbm

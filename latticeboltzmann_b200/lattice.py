@@ -69,6 +69,10 @@ class Block:
     def set_halo_timeout_ms(self, ms):
         check(self.lib.lb_set_halo_timeout_ms(self.h, int(ms)))
 
+    def set_temporal(self, steps_per_pass, rows_per_tile=0):
+        """1: single-step kernel; 2: temporal blocking, two time steps per pass over HBM (bit-identical)."""
+        check(self.lib.lb_set_temporal(self.h, int(steps_per_pass), int(rows_per_tile)))
+
     def set_use_graph(self, on):
         check(self.lib.lb_set_use_graph(self.h, int(bool(on))))
 
