@@ -239,6 +239,8 @@ def main():
     ap.add_argument("--workload", default="weak16384", choices=["weak16384", "cavity4096", "strong32768"])
     ap.add_argument("--arith", default="exact", choices=["fast", "exact"],
                     help="exact: bit-identical to the reference's no-FMA build (default); fast: FMA contraction, <1e-12")
+    ap.add_argument("--temporal", type=int, default=2, choices=[1, 2],
+                    help="time steps per pass over HBM: 2 = temporal blocking (default, bit-identical), 1 = single-step kernel")
     ap.add_argument("--rows-per-tile", type=int, default=0)
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -261,7 +263,8 @@ def main():
     rank, world, local_rank = D.init_process_group("nccl")
     numa = D.bind_to_gpu_numa(local_rank) if world > 1 else None      # pinned e2e buffers next to their GPU
     lat = D.DistributedLattice(nx, ny, ndx, ndy, "cavity", omega=omega, u_wall=0.1, dtype=np.float64,
-                               arith=args.arith, device=local_rank, rows_per_tile=args.rows_per_tile or None)
+                               arith=args.arith, device=local_rank, rows_per_tile=args.rows_per_tile or None,
+                               temporal=args.temporal)
     lat.init_equilibrium()
     lat.step(args.warmup)
     lat.sync()
@@ -280,12 +283,18 @@ def main():
 
     cells = nx * ny
     mlups = cells * args.steps / (ms * 1e-3) / 1e6
-    # roofline of the dominant (only) kernel of the step: one launch updates this rank's block
+    # Roofline of the dominant kernel.  One PASS over the block reads 72 B and writes 72 B per cell
+    # (fp64): with the single-step kernel a pass is one time step (one launch); with temporal blocking a
+    # pass is TWO time steps (the fused deep-interior kernel plus two perimeter-sized frame kernels).
     b = lat.blockinfo
-    per_launch_ms = ms / args.steps
-    achieved = b.lnx * b.lny * BYTES_PER_CELL / (per_launch_ms * 1e-3) / 1e9
+    t2 = args.temporal == 2 and lat.block.temporal_active
+    steps_per_pass = 2 if t2 else 1
+    passes = args.steps // steps_per_pass + (args.steps % steps_per_pass)
+    per_step_ms = ms / args.steps
+    per_pass_ms = ms / passes
+    achieved = b.lnx * b.lny * BYTES_PER_CELL / (per_pass_ms * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
-    traffic = ncu_traffic_per_launch(args.arith, b.lnx * b.lny)
+    traffic = ncu_traffic_per_launch(args.arith + ("+t2" if t2 else ""), b.lnx * b.lny)
 
     e2e = None
     need = 9 * b.lnx * b.lny * 8 * world
@@ -319,16 +328,20 @@ def main():
     lat.close()
     if rank == 0:
         line = {"metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
-                "warmup": args.warmup, "ms_per_step": per_launch_ms, "higher_is_better": True, "scaling": scaling,
+                "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc, "nx": nx, "ny": ny, "ndx": ndx, "ndy": ndy, "omega": omega, "u0": 0.1,
-                           "arith": args.arith, "halo": "in-kernel peer stores over NVLink (CUDA IPC), device-side flags",
+                           "arith": args.arith, "steps_per_hbm_pass": steps_per_pass,
+                           "single_step_roofline_mlups": peak * 1e9 / BYTES_PER_CELL / 1e6,
+                           "halo": "in-kernel peer stores over NVLink (CUDA IPC), device-side flags",
                            "numa_bound_cpus": (len(numa) if numa else None),
                            "l2": "inputs larger than L2 (%.1f GB per buffer per GPU, A/B ping-pong)" % (9 * b.lnx * b.lny * 8 / 1e9)},
                 "clocks": clocks, "e2e": e2e, "gpu_launches": launches * world,
                 "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                              "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
-                             "bytes_per_cell": BYTES_PER_CELL, "cells_per_launch": b.lnx * b.lny,
+                             "bytes_per_cell_per_pass": BYTES_PER_CELL, "steps_per_pass": steps_per_pass,
+                             "cells_per_launch": b.lnx * b.lny, "ms_per_pass": per_pass_ms,
+                             "kernel": "t2_interior_kernel (+ 2 frame kernels per pass)" if t2 else "step_kernel",
                              "traffic_note": (traffic or {}).get("note")},
                 "cpu_baseline": cpu}
         emit(line)

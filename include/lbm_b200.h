@@ -174,10 +174,17 @@ LB_API int lb_set_rows_per_tile(lb_lattice *lat, int rows);
 /* How long a rim CTA waits for a neighbour's halo flag before the lattice is marked failed
  * (lb_health -> LB_ERR_HALO_TIMEOUT) instead of hanging the GPU.  Default 20 s.            */
 LB_API int lb_set_halo_timeout_ms(lb_lattice *lat, int64_t ms);
-/* Time steps per pass over HBM: 1 = the single-step kernel, 2 = temporal blocking (two steps per
- * pass, bit-identical results; periodic / cavity boundaries, blocks of at least 16 x 16 cells).
- * rows_per_tile > 0 overrides the fused tile height (default 64).                               */
+/* Time steps per pass over HBM: 2 (default) = temporal blocking, lb_step advances pairs of steps
+ * with one read and one write of the lattice (bit-identical results; periodic / cavity boundaries,
+ * blocks of at least 16 x 16 cells, odd remainders and everything else use the single-step kernel);
+ * 1 = always the single-step kernel.  rows_per_tile > 0 overrides the fused tile height (default 32).
+ * Environment override: LBM_TEMPORAL=1|2.                                                        */
 LB_API int lb_set_temporal(lb_lattice *lat, int steps_per_pass, int rows_per_tile);
+/* One phase (1, 2, 3) of a temporal-blocking double step, for drivers that run several blocks on ONE
+ * stream: phase 3 of a block waits for phase 1 of its neighbours, so the phases of all blocks must be
+ * interleaved.  lb_temporal_active tells whether lb_step uses double steps for this lattice.       */
+LB_API int lb_double_step_phase(lb_lattice *lat, int phase);
+LB_API int lb_temporal_active(lb_lattice *lat);
 /* lb_step replays a CUDA graph of 64 fused steps for long runs (default on).                */
 LB_API int lb_set_use_graph(lb_lattice *lat, int on);
 /* Geometry queries (elements). */

@@ -40,8 +40,11 @@ struct lb_lattice {
     cudaStream_t graph_stream = nullptr;
     int graph_rows_per_tile = 0;
     bool use_graph = true;
-    int temporal = 1;            // time steps per pass over HBM: 1 (single-step kernel) or 2 (temporal.cuh)
-    int t2_rows = 64;
+    int temporal = 2;            // time steps per pass over HBM: 1 (single-step kernel) or 2 (temporal.cuh, default)
+    int t2_rows = 32;
+    cudaGraphExec_t graph2_exec = nullptr;   // GRAPH_DOUBLE double steps
+    cudaStream_t graph2_stream = nullptr;
+    int graph2_rows = 0;
     int64_t steps = 0;
     int cur = 0;                 // host mirror of DevState::cur (buffer holding the current state)
     int64_t launches = 0;
@@ -84,6 +87,8 @@ void drop_graph(lb_lattice *L)
 {
     if (L->graph_exec) cudaGraphExecDestroy(L->graph_exec);
     L->graph_exec = nullptr;
+    if (L->graph2_exec) cudaGraphExecDestroy(L->graph2_exec);
+    L->graph2_exec = nullptr;
 }
 
 DevState *dev_state(lb_lattice *L) { return reinterpret_cast<DevState *>(L->base + L->state_off); }
@@ -188,7 +193,7 @@ int launch_step(lb_lattice *L, bool collide)
 
 // One double step (temporal.cuh): frame level n+1, fused deep interior, frame level n+2.
 template <typename T, int BC, bool EXACT>
-int launch_double_bc(lb_lattice *L, const StepParams<T> &p)
+int launch_double_bc(lb_lattice *L, const StepParams<T> &p, int phases = 7)
 {
     static bool attr_set[64] = {};           // per device: the fused tile's shared-memory ring exceeds the 48 KB default
     const int dev = L->cfg.device & 63;
@@ -198,27 +203,56 @@ int launch_double_bc(lb_lattice *L, const StepParams<T> &p)
     }
     const int g1 = (int)((ring_cells(p.lnx, p.lny, FRAME_W) + TILE_L - 1) / TILE_L);
     const int g3 = (int)((ring_cells(p.lnx, p.lny, 2) + TILE_L - 1) / TILE_L);
-    t2_frame1_kernel<T, BC, EXACT><<<g1, TILE_L, 0, L->stream>>>(p);
-    t2_interior_kernel<T, BC, EXACT><<<p.t2_tiles_l * p.t2_tiles_k, TILE_L, t2_smem_bytes<T>(), L->stream>>>(p);
-    t2_frame2_kernel<T, BC, EXACT><<<g3, TILE_L, 0, L->stream>>>(p);
+    if (phases & 1) t2_frame1_kernel<T, BC, EXACT><<<g1, TILE_L, 0, L->stream>>>(p);
+    if (phases & 2) t2_interior_kernel<T, BC, EXACT><<<p.t2_tiles_l * p.t2_tiles_k, T2_TILE, t2_smem_bytes<T>(), L->stream>>>(p);
+    if (phases & 4) t2_frame2_kernel<T, BC, EXACT><<<g3, TILE_L, 0, L->stream>>>(p);
     return 0;
 }
 
 template <typename T>
-int launch_double(lb_lattice *L)
+int launch_double(lb_lattice *L, int phases = 7)
 {
     const StepParams<T> p = make_params<T>(L);
     const bool exact = L->cfg.arith == LB_ARITH_EXACT;
     switch (L->cfg.boundary) {
     case LB_PERIODIC:
-        return exact ? launch_double_bc<T, BC_PERIODIC, true>(L, p) : launch_double_bc<T, BC_PERIODIC, false>(L, p);
+        return exact ? launch_double_bc<T, BC_PERIODIC, true>(L, p, phases) : launch_double_bc<T, BC_PERIODIC, false>(L, p, phases);
     case LB_CAVITY:
-        return exact ? launch_double_bc<T, BC_CAVITY, true>(L, p) : launch_double_bc<T, BC_CAVITY, false>(L, p);
+        return exact ? launch_double_bc<T, BC_CAVITY, true>(L, p, phases) : launch_double_bc<T, BC_CAVITY, false>(L, p, phases);
     case LB_CAVITY_XPERIODIC:
-        return exact ? launch_double_bc<T, BC_CAVITY_XPERIODIC, true>(L, p) : launch_double_bc<T, BC_CAVITY_XPERIODIC, false>(L, p);
+        return exact ? launch_double_bc<T, BC_CAVITY_XPERIODIC, true>(L, p, phases) : launch_double_bc<T, BC_CAVITY_XPERIODIC, false>(L, p, phases);
     default:
         return lbm_fail(LB_ERR_INVALID, "temporal blocking supports the periodic and cavity boundaries");
     }
+}
+
+constexpr int GRAPH_DOUBLE = 32;     // double steps per graph launch (64 time steps)
+
+int ensure_graph2(lb_lattice *L)
+{
+    if (L->graph2_exec && L->graph2_stream == L->stream && L->graph2_rows == L->t2_rows) return 0;
+    if (L->graph2_exec) cudaGraphExecDestroy(L->graph2_exec);
+    L->graph2_exec = nullptr;
+    // first launch outside the capture: it sets the kernels' shared-memory attribute
+    cudaGraph_t g = nullptr;
+    LBM_CUDA(cudaStreamBeginCapture(L->stream, cudaStreamCaptureModeThreadLocal));
+    int r = 0;
+    for (int s = 0; s < GRAPH_DOUBLE && !r; ++s) r = L->cfg.dtype == LB_F64 ? launch_double<double>(L) : launch_double<float>(L);
+    cudaError_t e = cudaStreamEndCapture(L->stream, &g);
+    if (r || e != cudaSuccess) {
+        if (g) cudaGraphDestroy(g);
+        cudaGetLastError();
+        return r ? r : lbm_fail(LB_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    }
+    e = cudaGraphInstantiate(&L->graph2_exec, g, 0);
+    cudaGraphDestroy(g);
+    if (e != cudaSuccess) {
+        L->graph2_exec = nullptr;
+        return lbm_fail(LB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
+    }
+    L->graph2_stream = L->stream;
+    L->graph2_rows = L->t2_rows;
+    return 0;
 }
 
 bool temporal_ok(const lb_lattice *L)
@@ -333,7 +367,7 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
         return lbm_fail(LB_ERR_CUDA, "lattice set-up failed: %s", cudaGetErrorString(e));
     }
     L->rows_per_tile = cfg->dtype == LB_F64 ? 4 : 8;     // measured optima
-    if (const char *t = getenv("LBM_TEMPORAL")) L->temporal = atoi(t) == 2 ? 2 : 1;
+    if (const char *t = getenv("LBM_TEMPORAL")) L->temporal = atoi(t) == 1 ? 1 : 2;
     if (const char *t = getenv("LBM_T2_ROWS")) if (atoi(t) > 0) L->t2_rows = atoi(t);
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
@@ -389,6 +423,29 @@ int lb_set_halo_timeout_ms(lb_lattice *L, int64_t ms)
     drop_graph(L);      // the timeout is a launch argument
     return 0;
 }
+
+/* One phase of a double step (1: frame level n+1, 2: fused deep interior, 3: frame level n+2, which
+ * completes the step).  For drivers that run several blocks on ONE stream: the phases of all blocks must be
+ * interleaved (all 1s, all 2s, all 3s), because phase 3 of a block waits for phase 1 of its neighbours. */
+int lb_double_step_phase(lb_lattice *L, int phase)
+{
+    if (int r = check_ready(L)) return r;
+    if (phase < 1 || phase > 3) return lbm_fail(LB_ERR_INVALID, "phase must be 1, 2 or 3");
+    if (!temporal_ok(L)) return lbm_fail(LB_ERR_STATE, "temporal blocking is not available for this lattice");
+    LBM_ON_DEVICE(L);
+    int r = L->cfg.dtype == LB_F64 ? launch_double<double>(L, 1 << (phase - 1)) : launch_double<float>(L, 1 << (phase - 1));
+    if (r) return r;
+    L->launches++;
+    if (phase == 3) {
+        L->steps += 2;
+        L->cur ^= 1;
+    }
+    LBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+/* 1 if lb_step advances this lattice two steps per pass (temporal blocking), else 0. */
+int lb_temporal_active(lb_lattice *L) { return L && temporal_ok(L) ? 1 : 0; }
 
 int lb_set_temporal(lb_lattice *L, int steps_per_pass, int rows_per_tile)
 {
@@ -584,6 +641,22 @@ int lb_step(lb_lattice *L, int64_t nsteps)
     const bool sf = L->cfg.boundary >= LB_SF_COUETTE;
     // Temporal blocking: two steps per pass over HBM (three launches per double step).
     if (temporal_ok(L)) {
+        if (L->use_graph && nsteps >= 4 * GRAPH_DOUBLE) {
+            // one eager double step first: it sets the fused kernel's shared-memory attribute outside any capture
+            int r = L->cfg.dtype == LB_F64 ? launch_double<double>(L) : launch_double<float>(L);
+            if (r) return r;
+            L->launches += 3;
+            L->steps += 2;
+            L->cur ^= 1;
+            nsteps -= 2;
+            if ((r = ensure_graph2(L))) return r;
+            while (nsteps >= 2 * GRAPH_DOUBLE) {
+                LBM_CUDA(cudaGraphLaunch(L->graph2_exec, L->stream));
+                L->launches += 3 * GRAPH_DOUBLE;
+                L->steps += 2 * GRAPH_DOUBLE;          // GRAPH_DOUBLE buffer flips: an even number
+                nsteps -= 2 * GRAPH_DOUBLE;
+            }
+        }
         while (nsteps >= 2) {
             int r = L->cfg.dtype == LB_F64 ? launch_double<double>(L) : launch_double<float>(L);
             if (r) return r;

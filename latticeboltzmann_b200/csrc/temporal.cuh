@@ -29,11 +29,30 @@
 
 namespace lbm {
 
-constexpr int T2_W = TILE_L - 2;      // output columns per fused tile (256 level-(n+1) columns incl. halo)
-constexpr int T2_SLOTS = 4;           // shared-memory ring of level-(n+1) rows
+#ifndef LBM_T2_TILE
+#define LBM_T2_TILE 256
+#endif
+constexpr int T2_TILE = LBM_T2_TILE;  // threads (= level-(n+1) columns incl. the one-cell halo) per fused tile
+constexpr int T2_W = T2_TILE - 2;     // level-(n+2) output columns per fused tile
+#ifndef LBM_T2_SLOTS
+#define LBM_T2_SLOTS 4
+#endif
+// Measured at 16384^2 fp64 EXACT (GLUPS): all 9 populations through the ring, 3 CTAs/SM: 61.5; six-population
+// ring + register-kept rest/E/W with row prefetch at 80 registers / 3 CTAs: 58.8; the same WITHOUT prefetch at
+// 64 registers / 4 CTAs (32 warps): 78.1; 128-thread tiles: 60-61.  Occupancy, not prefetch depth, is what
+// hides the latency of the two collisions per row.
+#ifndef LBM_T2_PREFETCH
+#define LBM_T2_PREFETCH 0
+#endif
+#ifndef LBM_T2_MINB
+#define LBM_T2_MINB 4
+#endif
+constexpr int T2_SLOTS = LBM_T2_SLOTS;   // shared-memory ring of level-(n+1) rows (4: one barrier per row; 3: two)
 
 template <typename T>
-__host__ __device__ constexpr int t2_smem_bytes() { return T2_SLOTS * 9 * TILE_L * (int)sizeof(T); }
+__host__ __device__ constexpr int t2_smem_bytes() { return T2_SLOTS * 6 * T2_TILE * (int)sizeof(T); }
+// ring slot of the six populations that shift in y (0, E, W stay in the thread's registers)
+__host__ __device__ constexpr int ring_pop(int i) { return i == 2 ? 0 : i == 4 ? 1 : i - 3; }   // N,S,NE,NW,SW,SE -> 0..5
 
 // cells closer than w to the perimeter (needs lnx, lny >= 2w)
 __host__ __device__ inline long long ring_cells(int lnx, int lny, int w) { return 2ll * w * lny + 2ll * w * (lnx - 2 * w); }
@@ -270,13 +289,14 @@ __global__ void __launch_bounds__(TILE_L) t2_frame2_kernel(const __grid_constant
     }
 }
 
-// K2: level n -> n+2 on the deep interior through a shared-memory ring of level-(n+1) rows.
+// K2: level n -> n+2 on the deep interior.  Level-(n+1) rows stream through the tile: the six populations
+// that shift in y go through a shared-memory ring (neighbouring threads consume them), the three that do not
+// (rest, E, W: consumed by the SAME thread one row later / earlier) stay in registers.
 template <typename T, int BC, bool EXACT>
-__global__ void __launch_bounds__(TILE_L) t2_interior_kernel(const __grid_constant__ StepParams<T> p)
+__global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const __grid_constant__ StepParams<T> p)
 {
     extern __shared__ __align__(16) unsigned char t2_smem_raw[];
-    T *ring = reinterpret_cast<T *>(t2_smem_raw);               // [T2_SLOTS][9][TILE_L]
-    const unsigned long long step = *(volatile unsigned long long *)&p.st->step;
+    T *ring = reinterpret_cast<T *>(t2_smem_raw);               // [T2_SLOTS][6][T2_TILE]
     const int par = (int)*(volatile unsigned int *)&p.st->cur;
     const T *__restrict__ src = p.buf[par];
     T *__restrict__ dst = p.buf[par ^ 1];
@@ -291,35 +311,63 @@ __global__ void __launch_bounds__(TILE_L) t2_interior_kernel(const __grid_consta
     const long long row_bytes = p.pitch * (long long)sizeof(T);
     const char *sp = reinterpret_cast<const char *>(src + (long long)k0 * p.pitch + (lc + PAD_L));        // row k0-1
     T *dp = dst + (long long)(k0 + 1) * p.pitch + (lc + PAD_L);                                           // row k0
+    T rest_m1 = T(0), e_m1 = T(0), e_m2 = T(0);                 // level n+1: rest of row j-1, E of rows j-1 and j-2
+#if LBM_T2_PREFETCH
+    T nxt[9];
+    if (have1) interior_load<T>(p, sp, nxt);                     // row k0-1 in flight
+#endif
 #pragma unroll 1
     for (int j = k0 - 1; j <= k1; ++j) {
-        if (have1) {
-            T f[9];
-            interior_load<T>(p, sp, f);
-            d2q9_collide<T, EXACT>(f, p.omega);
-            T *slot = ring + (long long)(j & (T2_SLOTS - 1)) * 9 * TILE_L + t;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) slot[i * TILE_L] = f[i];
-        }
         sp += row_bytes;
+        T f[9];
+        if (have1) {
+#if LBM_T2_PREFETCH
+#pragma unroll
+            for (int i = 0; i < 9; ++i) f[i] = nxt[i];
+            if (j < k1) interior_load<T>(p, sp, nxt);            // next row's loads overlap this row's two collisions
+#else
+            interior_load<T>(p, sp - row_bytes, f);
+#endif
+            d2q9_collide<T, EXACT>(f, p.omega);
+            T *slot = ring + (long long)(j % T2_SLOTS) * 6 * T2_TILE + t;
+            slot[ring_pop(QN) * T2_TILE] = f[QN];
+            slot[ring_pop(QS) * T2_TILE] = f[QS];
+            slot[ring_pop(QNE) * T2_TILE] = f[QNE];
+            slot[ring_pop(QNW) * T2_TILE] = f[QNW];
+            slot[ring_pop(QSW) * T2_TILE] = f[QSW];
+            slot[ring_pop(QSE) * T2_TILE] = f[QSE];
+        }
         __syncthreads();
-        if (j >= k0 + 1) {                                       // level-(n+1) rows j-2, j-1, j are in the ring: emit row j-1
+        const T rest_0 = f[Q0], e_0 = f[QE], w_0 = f[QW];       // level n+1, row j, this column
+        if (j >= k0 + 1) {                                       // level-(n+1) rows j-2, j-1, j are available: emit row j-1
             if (have2) {
                 const int jo = j - 1;
-                T f[9];
-#pragma unroll
-                for (int i = 0; i < 9; ++i)
-                    f[i] = ring[((long long)((jo - cx_of(i)) & (T2_SLOTS - 1)) * 9 + i) * TILE_L + (t - cy_of(i))];
-                d2q9_collide<T, EXACT>(f, p.omega);
+                T g[9];
+                g[Q0] = rest_m1;                                 // (jo, lc)
+                g[QE] = e_m2;                                    // pulled from row jo-1
+                g[QW] = w_0;                                     // pulled from row jo+1
+#define LBM_RING(I) ring[((long long)((jo - cx_of(I)) % T2_SLOTS) * 6 + ring_pop(I)) * T2_TILE + (t - cy_of(I))]
+                g[QN] = LBM_RING(QN);
+                g[QS] = LBM_RING(QS);
+                g[QNE] = LBM_RING(QNE);
+                g[QNW] = LBM_RING(QNW);
+                g[QSW] = LBM_RING(QSW);
+                g[QSE] = LBM_RING(QSE);
+#undef LBM_RING
+                d2q9_collide<T, EXACT>(g, p.omega);
                 T *q = dp;
 #pragma unroll
                 for (int i = 0; i < 9; ++i) {
-                    *q = f[i];
+                    *q = g[i];
                     q += p.pop_stride;
                 }
             }
             dp += p.pitch;
         }
+        e_m2 = e_m1;
+        e_m1 = e_0;
+        rest_m1 = rest_0;
+        if (T2_SLOTS < 4) __syncthreads();                       // 3 slots: row j+1 overwrites the slot of row j-2 just read
     }
 }
 

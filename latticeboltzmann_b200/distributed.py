@@ -102,7 +102,7 @@ class DistributedLattice:
     (rank = px*ndy + py, as Create_cart numbers them)."""
 
     def __init__(self, nx, ny, ndx, ndy, boundary="cavity", omega=1.0, u_wall=0.1, dtype=np.float64,
-                 arith="exact", device=None, group=None, rows_per_tile=None):
+                 arith="exact", device=None, group=None, rows_per_tile=None, temporal=None):
         dist = _dist()
         self.group = group
         self.rank = dist.get_rank(group)
@@ -117,6 +117,8 @@ class DistributedLattice:
         self.block = Block(nx, ny, b.x0, b.y0, b.lnx, b.lny, boundary, omega, u_wall, dtype, arith, device)
         if rows_per_tile:
             self.block.set_rows_per_tile(rows_per_tile)
+        if temporal:
+            self.block.set_temporal(temporal)
         blobs = exchange_blobs(bytes(self.block.export()), group)
         self.exports = [LbExport.from_buffer_copy(x) for x in blobs]
         for d, nb in enumerate(self.decomp.neighbours(self.rank)):

@@ -73,6 +73,13 @@ class Block:
         """1: single-step kernel; 2: temporal blocking, two time steps per pass over HBM (bit-identical)."""
         check(self.lib.lb_set_temporal(self.h, int(steps_per_pass), int(rows_per_tile)))
 
+    def double_step_phase(self, phase):
+        check(self.lib.lb_double_step_phase(self.h, int(phase)))
+
+    @property
+    def temporal_active(self):
+        return bool(self.lib.lb_temporal_active(self.h))
+
     def set_use_graph(self, on):
         check(self.lib.lb_set_use_graph(self.h, int(bool(on))))
 
@@ -168,7 +175,7 @@ class Lattice:
     """
 
     def __init__(self, nx, ny, boundary="periodic", omega=1.0, u_wall=0.1, dtype=np.float64, arith="exact",
-                 ndx=1, ndy=1, devices=0, rho_in=1.0, rho_out=1.0, rows_per_tile=None):
+                 ndx=1, ndy=1, devices=0, rho_in=1.0, rho_out=1.0, rows_per_tile=None, temporal=None):
         self.nx, self.ny = int(nx), int(ny)
         self.dtype = np.dtype(dtype)
         self.boundary = boundary
@@ -187,6 +194,9 @@ class Lattice:
         if rows_per_tile:
             for blk in self.blocks:
                 blk.set_rows_per_tile(rows_per_tile)
+        if temporal:                         # 1: single-step kernel only; 2: two steps per HBM pass (library default)
+            for blk in self.blocks:
+                blk.set_temporal(temporal)
         exports = [blk.export() for blk in self.blocks]
         for r, blk in enumerate(self.blocks):
             for d, nb in enumerate(self.decomp.neighbours(r)):
@@ -252,7 +262,15 @@ class Lattice:
         if len(self.blocks) == 1:
             self.blocks[0].step(n)
         else:
-            for _ in range(n):
+            # Blocks that share a device share a stream, so launches are interleaved such that every flag a
+            # kernel waits for is posted by a launch already queued: double steps phase by phase (phase 3 of a
+            # block waits for phase 1 of its neighbours), single steps block by block.
+            pairs = n // 2 if all(b.temporal_active for b in self.blocks) else 0
+            for _ in range(pairs):
+                for phase in (1, 2, 3):
+                    for b in self.blocks:
+                        b.double_step_phase(phase)
+            for _ in range(n - 2 * pairs):
                 for b in self.blocks:
                     b.step(1)
 

@@ -79,8 +79,8 @@ def test_cavity_1000_steps_exact_and_fast():
     ref = orc.init_equilibrium(nx, ny)
     orc.cavity_run(ref, omega, 1000)
     rr, rux, ruy = orc.moments(ref)
-    for arith in ("exact", "fast"):
-        lat = lb.Lattice(nx, ny, "cavity", omega=omega, u_wall=0.1, arith=arith)
+    for arith, temporal in (("exact", 2), ("exact", 1), ("fast", 2)):
+        lat = lb.Lattice(nx, ny, "cavity", omega=omega, u_wall=0.1, arith=arith, temporal=temporal)
         lat.init_equilibrium()
         lat.step(1000)
         f = lat.download()
@@ -108,6 +108,31 @@ def test_cavity_vs_reference_opt1_golden(golden_dir):
         done = n
         assert rel_err(lat.download(), g["f_%d" % n]) < 1e-12, n
     lat.close()
+
+
+@pytest.mark.parametrize("temporal", [1, 2])
+@pytest.mark.parametrize("boundary", ["periodic", "cavity", "cavity_xperiodic"])
+@pytest.mark.parametrize("ndx,ndy", [(2, 1), (1, 2), (2, 2), (3, 2)])
+def test_decomposition_bit_exact_larger_blocks(boundary, ndx, ndy, temporal):
+    """Blocks large enough (>= 16 x 16) for the temporal-blocking double step: the level-(n+1) frame ghosts
+    are exchanged between blocks as well.  Odd step counts mix double and single steps."""
+    lb = require_gpu()
+    nx, ny = 101, 83
+    f0 = orc.perturbed_state(nx, ny, seed=12)
+    ref = f0.copy()
+    if boundary == "periodic":
+        orc.periodic_run(ref, 1.7, 31)
+    else:
+        orc.cavity_run(ref, 1.7, 31, 0.1, walls_lr=(boundary == "cavity"))
+    lat = lb.Lattice(nx, ny, boundary, omega=1.7, ndx=ndx, ndy=ndy, temporal=temporal)
+    assert all(b.temporal_active == (temporal == 2) for b in lat.blocks)
+    lat.upload(f0)
+    lat.step(14)
+    lat.step(17)
+    got = lat.download()
+    lat.health()
+    lat.close()
+    assert np.array_equal(got, ref)
 
 
 @pytest.mark.parametrize("boundary", ["periodic", "cavity", "cavity_xperiodic"])
@@ -225,8 +250,8 @@ def test_graph_replay_equals_single_launches():
     lb = require_gpu()
     f0 = orc.perturbed_state(70, 530, seed=5)
     outs = []
-    for use_graph in (True, False):
-        lat = lb.Lattice(70, 530, "cavity", omega=1.7)
+    for use_graph, temporal in ((True, 1), (False, 1), (True, 2), (False, 2)):
+        lat = lb.Lattice(70, 530, "cavity", omega=1.7, temporal=temporal)
         lat.blocks[0].set_use_graph(use_graph)
         lat.upload(f0)
         lat.step(64 * 3 + 17)
@@ -234,7 +259,7 @@ def test_graph_replay_equals_single_launches():
         assert lat.kernel_launches >= 64 * 3 + 17
         lat.health()
         lat.close()
-    assert np.array_equal(outs[0], outs[1])
+    assert all(np.array_equal(outs[0], o) for o in outs[1:])
     ref = f0.copy()
     orc.cavity_run(ref, 1.7, 64 * 3 + 17)
     assert np.array_equal(outs[0], ref)
