@@ -13,6 +13,9 @@ Workloads (BASELINE.json configs):
   cavity4096   lid-driven cavity 4096 x 4096, Re = 1000, one GPU (configs[2])
   strong32768  lid-driven cavity 32768 x 32768 split over N GPUs (configs[3], strong scaling)
 
+Stepping mode: `--temporal 2` (default) advances two time steps per pass over HBM (temporal blocking,
+bit-identical to single steps); `--temporal 1` times the single-step kernel (one pass per step).
+
 One JSON line on stdout (rank 0).  `value` = whole-job MLUPS with the state resident in HBM;
 `e2e` = the same step driven through the host-buffer C-ABI path (pinned host f in, f out,
 every step); `roofline` = the step kernel against the measured HBM peak; `cpu_baseline` =
