@@ -194,7 +194,13 @@ class Lattice:
         if rows_per_tile:
             for blk in self.blocks:
                 blk.set_rows_per_tile(rows_per_tile)
-        if temporal:                         # 1: single-step kernel only; 2: two steps per HBM pass (library default)
+        # 1: single-step kernel only; 2: two steps per HBM pass (library default).  Temporal blocking is a
+        # collective property of the decomposition (a block waits for its neighbours' level-(n+1) frame ghosts):
+        # if any block is too small for it, every block uses the single-step kernel.
+        if temporal == 1 or not all(b.lnx >= 16 and b.lny >= 16 for b in self.decomp.blocks()):
+            for blk in self.blocks:
+                blk.set_temporal(1)
+        elif temporal:
             for blk in self.blocks:
                 blk.set_temporal(temporal)
         exports = [blk.export() for blk in self.blocks]

@@ -75,3 +75,15 @@ def test_decomposition_rank_layout_and_rings():
     assert (cover == 1).all()
     one = Decomposition(9, 9, 1, 1)
     assert one.neighbours(0) == [0] * 8
+
+
+def test_temporal_blocking_eligibility_is_collective():
+    """A decomposition uses temporal blocking only if EVERY block is at least 16 x 16 (host-side rule that
+    DistributedLattice / Lattice apply before stepping; a mixed world would dead-wait on frame-ghost flags)."""
+    ok = Decomposition(64, 64, 2, 2)
+    assert all(b.lnx >= 16 and b.lny >= 16 for b in ok.blocks())
+    mixed = Decomposition(53, 47, 8, 1)          # 6- and 11-row slabs
+    assert not all(b.lnx >= 16 and b.lny >= 16 for b in mixed.blocks())
+    rem = Decomposition(47, 64, 3, 1)            # 15, 15, 17: the remainder block alone would be eligible
+    assert [b.lnx for b in rem.blocks()] == [15, 15, 17]
+    assert not all(b.lnx >= 16 for b in rem.blocks())
