@@ -110,6 +110,10 @@ typedef struct lb_export {
 
 LB_API const char *lb_last_error(void);
 LB_API int lb_abi_version(void);
+/* sizeof(lb_config) / sizeof(lb_export) as compiled into the library, for bindings to verify their struct
+ * declarations against (a mismatch would silently corrupt the halo wiring).                       */
+LB_API int64_t lb_sizeof_config(void);
+LB_API int64_t lb_sizeof_export(void);
 LB_API int lb_device_count(void);
 
 /* ---- (2) device-resident lattice ------------------------------------------------ */

@@ -47,6 +47,8 @@ _P = ctypes.POINTER
 SYMBOLS = {
     "lb_last_error": (ctypes.c_char_p, []),
     "lb_abi_version": (ctypes.c_int, []),
+    "lb_sizeof_config": (c_i64, []),
+    "lb_sizeof_export": (c_i64, []),
     "lb_device_count": (ctypes.c_int, []),
     "lb_create": (ctypes.c_int, [_P(LbConfig), _P(c_vp)]),
     "lb_destroy": (ctypes.c_int, [c_vp]),
@@ -116,6 +118,8 @@ def load(build_if_missing=True):
         fn = getattr(lib, name)   # AttributeError if the ABI is incomplete
         fn.restype = res
         fn.argtypes = args
+    if lib.lb_sizeof_config() != ctypes.sizeof(LbConfig) or lib.lb_sizeof_export() != ctypes.sizeof(LbExport):
+        raise LbmError("ctypes declarations of lb_config / lb_export do not match %s (rebuild the library)" % path)
     _lib = lib
     return lib
 

@@ -16,3 +16,6 @@ extern "C" int lbm_fail(int code, const char *fmt, ...)
 }
 
 extern "C" const char *lb_last_error(void) { return g_err; }
+
+extern "C" int64_t lb_sizeof_config(void) { return (int64_t)sizeof(lb_config); }
+extern "C" int64_t lb_sizeof_export(void) { return (int64_t)sizeof(lb_export); }

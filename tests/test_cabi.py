@@ -26,7 +26,11 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
         assert hasattr(lib, n), n
     # the ctypes table binds exactly the declared ABI
     assert sorted(_lib.SYMBOLS) == names
-    assert _lib.load().lb_abi_version() == 1
+    lib2 = _lib.load()
+    assert lib2.lb_abi_version() == 1
+    # the ctypes mirrors of the ABI structs have the C layout (the export struct carries the halo wiring)
+    assert lib2.lb_sizeof_config() == ctypes.sizeof(_lib.LbConfig) == 96
+    assert lib2.lb_sizeof_export() == ctypes.sizeof(_lib.LbExport)
 
 
 def test_no_cpu_fallback_without_device():
