@@ -40,7 +40,7 @@ struct lb_lattice {
     cudaStream_t graph_stream = nullptr;
     int graph_rows_per_tile = 0;
     bool use_graph = true;
-    int temporal = 2;            // time steps per pass over HBM: 1 (single-step kernel) or 2 (temporal.cuh, default)
+    int temporal = 0;            // 0: auto (two steps per HBM pass when the block is big enough to fill the GPU), 1: single-step kernel, 2: force temporal blocking
     int t2_rows = 32;
     cudaGraphExec_t graph2_exec = nullptr;   // GRAPH_DOUBLE double steps
     cudaStream_t graph2_stream = nullptr;
@@ -255,9 +255,18 @@ int ensure_graph2(lb_lattice *L)
     return 0;
 }
 
+// Fused tiles a block must offer before the automatic mode prefers temporal blocking: below this the deep-
+// interior kernel cannot fill 148 SMs x 4 CTAs and the (latency-tuned, graph-replayed) single-step kernel wins.
+constexpr long long T2_AUTO_MIN_TILES = 1024;
+
 bool temporal_ok(const lb_lattice *L)
 {
-    return L->temporal == 2 && L->cfg.boundary <= LB_CAVITY_XPERIODIC && L->cfg.lnx >= 16 && L->cfg.lny >= 16 && !L->d_series;
+    if (L->temporal == 1) return false;
+    const bool eligible = L->cfg.boundary <= LB_CAVITY_XPERIODIC && L->cfg.lnx >= 16 && L->cfg.lny >= 16 && !L->d_series;
+    if (!eligible) return false;
+    if (L->temporal == 2) return true;
+    const long long tiles = ((L->cfg.lny - 4 + T2_W - 1) / T2_W) * ((L->cfg.lnx - 4 + L->t2_rows - 1) / L->t2_rows);
+    return tiles >= T2_AUTO_MIN_TILES;
 }
 
 // simple_flows step orders.  The pre-kernels rewrite the current buffer in
@@ -367,7 +376,7 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
         return lbm_fail(LB_ERR_CUDA, "lattice set-up failed: %s", cudaGetErrorString(e));
     }
     L->rows_per_tile = cfg->dtype == LB_F64 ? 4 : 8;     // measured optima
-    if (const char *t = getenv("LBM_TEMPORAL")) L->temporal = atoi(t) == 1 ? 1 : 2;
+    if (const char *t = getenv("LBM_TEMPORAL")) L->temporal = (atoi(t) >= 0 && atoi(t) <= 2) ? atoi(t) : 0;
     if (const char *t = getenv("LBM_T2_ROWS")) if (atoi(t) > 0) L->t2_rows = atoi(t);
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
@@ -449,7 +458,7 @@ int lb_temporal_active(lb_lattice *L) { return L && temporal_ok(L) ? 1 : 0; }
 
 int lb_set_temporal(lb_lattice *L, int steps_per_pass, int rows_per_tile)
 {
-    if (!L || (steps_per_pass != 1 && steps_per_pass != 2)) return lbm_fail(LB_ERR_INVALID, "steps_per_pass must be 1 or 2");
+    if (!L || steps_per_pass < 0 || steps_per_pass > 2) return lbm_fail(LB_ERR_INVALID, "steps_per_pass must be 0 (auto), 1 or 2");
     L->temporal = steps_per_pass;
     if (rows_per_tile > 0) L->t2_rows = rows_per_tile;
     return 0;

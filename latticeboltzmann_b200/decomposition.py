@@ -71,3 +71,25 @@ class Decomposition:
     def gather_into(self, g, rank, local):
         sx, sy = self.slices(rank)
         g[..., sx, sy] = local
+
+
+# ---- temporal blocking is a collective decision (csrc/temporal.cuh) -------------------------------------
+T2_MIN_EXTENT = 16            # a block needs at least 16 x 16 cells
+T2_TILE_COLS = 254            # output columns of a fused tile
+T2_TILE_ROWS = 32             # rows of a fused tile (library default)
+T2_AUTO_MIN_TILES = 1024      # automatic mode: fused tiles a block must offer to fill the GPU
+
+
+def temporal_mode(blocks, boundary, requested=None):
+    """The stepping mode every block of a decomposition must use: 2 (two time steps per pass over HBM) or 1
+    (single-step kernel).  A block waits for its neighbours' level-(n+1) frame ghosts, so the mode cannot be
+    mixed.  requested: None / 0 = automatic (temporal blocking only if the SMALLEST block still fills the
+    GPU), 1 = single-step, 2 = temporal blocking whenever every block is eligible."""
+    eligible = boundary in ("periodic", "cavity", "cavity_xperiodic") and all(
+        b.lnx >= T2_MIN_EXTENT and b.lny >= T2_MIN_EXTENT for b in blocks)
+    if requested == 1 or not eligible:
+        return 1
+    if requested == 2:
+        return 2
+    tiles = min(-(-(b.lny - 4) // T2_TILE_COLS) * -(-(b.lnx - 4) // T2_TILE_ROWS) for b in blocks)
+    return 2 if tiles >= T2_AUTO_MIN_TILES else 1

@@ -14,7 +14,7 @@ import os
 import numpy as np
 
 from ._lib import LbExport
-from .decomposition import Decomposition
+from .decomposition import Decomposition, temporal_mode
 from .lattice import Block
 
 
@@ -117,12 +117,9 @@ class DistributedLattice:
         self.block = Block(nx, ny, b.x0, b.y0, b.lnx, b.lny, boundary, omega, u_wall, dtype, arith, device)
         if rows_per_tile:
             self.block.set_rows_per_tile(rows_per_tile)
-        # Temporal blocking is a collective property: a rank that advances two steps per pass waits for its
-        # neighbours' level-(n+1) frame ghosts, so either every block of the decomposition is eligible
-        # (periodic / cavity boundary, at least 16 x 16 cells) or all ranks use the single-step kernel.
-        eligible = boundary in ("periodic", "cavity", "cavity_xperiodic") and all(
-            blk.lnx >= 16 and blk.lny >= 16 for blk in self.decomp.blocks())
-        self.block.set_temporal(temporal if (temporal and eligible) else (2 if eligible else 1))
+        # Temporal blocking is a collective property (a rank that advances two steps per pass waits for its
+        # neighbours' level-(n+1) frame ghosts): decide it for the whole decomposition and set it explicitly.
+        self.block.set_temporal(temporal_mode(self.decomp.blocks(), boundary, temporal))
         blobs = exchange_blobs(bytes(self.block.export()), group)
         self.exports = [LbExport.from_buffer_copy(x) for x in blobs]
         for d, nb in enumerate(self.decomp.neighbours(self.rank)):

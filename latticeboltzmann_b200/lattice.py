@@ -16,7 +16,7 @@ import numpy as np
 
 from . import _lib
 from ._lib import LbConfig, LbExport, check, np_ptr
-from .decomposition import Decomposition
+from .decomposition import Decomposition, temporal_mode
 
 
 class Block:
@@ -194,15 +194,11 @@ class Lattice:
         if rows_per_tile:
             for blk in self.blocks:
                 blk.set_rows_per_tile(rows_per_tile)
-        # 1: single-step kernel only; 2: two steps per HBM pass (library default).  Temporal blocking is a
-        # collective property of the decomposition (a block waits for its neighbours' level-(n+1) frame ghosts):
-        # if any block is too small for it, every block uses the single-step kernel.
-        if temporal == 1 or not all(b.lnx >= 16 and b.lny >= 16 for b in self.decomp.blocks()):
-            for blk in self.blocks:
-                blk.set_temporal(1)
-        elif temporal:
-            for blk in self.blocks:
-                blk.set_temporal(temporal)
+        # Stepping mode (1: single-step kernel, 2: two time steps per pass over HBM), decided for the whole
+        # decomposition: blocks that exchange halos cannot mix modes (decomposition.temporal_mode).
+        mode = temporal_mode(self.decomp.blocks(), boundary, temporal)
+        for blk in self.blocks:
+            blk.set_temporal(mode)
         exports = [blk.export() for blk in self.blocks]
         for r, blk in enumerate(self.blocks):
             for d, nb in enumerate(self.decomp.neighbours(r)):

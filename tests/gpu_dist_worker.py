@@ -18,7 +18,10 @@ def main():
     out, boundary, ndx, ndy, nx, ny, nsteps = sys.argv[1], sys.argv[2], *map(int, sys.argv[3:8])
     rank, world, local = D.init_process_group("nccl")
     f0 = orc.perturbed_state(nx, ny, seed=33)
-    lat = D.DistributedLattice(nx, ny, ndx, ndy, boundary, omega=1.7, u_wall=0.1, arith="exact", device=local)
+    # temporal=2: force the two-steps-per-pass mode (the automatic mode would pick the single-step kernel for
+    # blocks this small), so that the level-(n+1) frame-ghost exchange crosses NVLink as well
+    lat = D.DistributedLattice(nx, ny, ndx, ndy, boundary, omega=1.7, u_wall=0.1, arith="exact", device=local,
+                               temporal=2)
     lat.upload_global(f0)
     lat.step(nsteps)
     got = lat.gather_f()

@@ -77,6 +77,22 @@ def test_decomposition_rank_layout_and_rings():
     assert one.neighbours(0) == [0] * 8
 
 
+def test_temporal_mode_decision():
+    from latticeboltzmann_b200.decomposition import temporal_mode
+    big = Decomposition(16384 * 4, 16384 * 2, 4, 2).blocks()       # bench weak scaling at 8 GPUs
+    assert temporal_mode(big, "cavity") == 2 and temporal_mode(big, "cavity", 1) == 1
+    assert temporal_mode(Decomposition(4096, 4096).blocks(), "periodic") == 2
+    small = Decomposition(512, 512).blocks()
+    assert temporal_mode(small, "cavity") == 1                      # automatic: too few fused tiles to fill the GPU
+    assert temporal_mode(small, "cavity", 2) == 2                   # forced
+    assert temporal_mode(small, "sf_couette", 2) == 1               # simple_flows boundaries: single-step kernel
+    assert temporal_mode(Decomposition(53, 47, 8, 1).blocks(), "cavity", 2) == 1      # 6-row slabs are ineligible
+    # the smallest block decides: 65536 x 2900 split in 2 columns of 1450 -> 6 x 2048 tiles each, fine;
+    # split 40 ways in x -> blocks of 1638 rows x 2900: 52 x 12 = 624 tiles -> single-step for everybody
+    assert temporal_mode(Decomposition(65536, 2900, 1, 2).blocks(), "cavity") == 2
+    assert temporal_mode(Decomposition(65536, 2900, 40, 1).blocks(), "cavity") == 1
+
+
 def test_temporal_blocking_eligibility_is_collective():
     """A decomposition uses temporal blocking only if EVERY block is at least 16 x 16 (host-side rule that
     DistributedLattice / Lattice apply before stepping; a mixed world would dead-wait on frame-ghost flags)."""

@@ -57,7 +57,9 @@ def test_fused_step_bitexact_vs_oracle(dt, boundary):
                 lb.Lattice(nx, ny, boundary)
             continue
         f0 = orc.perturbed_state(nx, ny, np.dtype(dt), seed=nx * 1000 + ny)
-        lat = lb.Lattice(nx, ny, boundary, omega=1.7, u_wall=0.1, dtype=dt)
+        # temporal=2: blocks of at least 16 x 16 advance two steps per pass (7 steps = 3 double + 1 single),
+        # smaller ones fall back to the single-step kernel
+        lat = lb.Lattice(nx, ny, boundary, omega=1.7, u_wall=0.1, dtype=dt, temporal=2)
         lat.upload(f0)
         lat.step(7)
         got = lat.download()
@@ -273,7 +275,7 @@ def test_decomposition_bit_exact_fp32_and_reupload():
     ref = f0.copy()
     orc.cavity_run(ref, 1.7, 20)
     for ndx, ndy in ((1, 1), (3, 2)):
-        lat = lb.Lattice(nx, ny, "cavity", omega=1.7, dtype=np.float32, ndx=ndx, ndy=ndy)
+        lat = lb.Lattice(nx, ny, "cavity", omega=1.7, dtype=np.float32, ndx=ndx, ndy=ndy, temporal=2)
         lat.upload(f0)
         lat.step(9)
         mid = lat.download()
