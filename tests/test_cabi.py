@@ -53,3 +53,20 @@ def test_product_never_imports_oracle():
             if fn.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, fn)).read()
                 assert "oracle" not in txt.lower() or fn == "never", os.path.join(dp, fn)
+
+
+def test_plain_c_client_compiles_links_and_fails_loudly_without_gpu(tmp_path):
+    """examples/c_abi_cavity.c: the ABI is usable from plain C (no C++ / torch types in the header)."""
+    import subprocess
+    from latticeboltzmann_b200 import _lib
+    from latticeboltzmann_b200.build import build_native
+    so_dir = os.path.dirname(build_native())
+    exe = str(tmp_path / "c_abi_cavity")
+    subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"),
+                    os.path.join(ROOT, "examples", "c_abi_cavity.c"), "-o", exe, "-L", so_dir, "-llbm_b200",
+                    "-Wl,-rpath," + so_dir], check=True)
+    r = subprocess.run([exe, "64", "48", "20"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    if _lib.load().lb_device_count() > 0:
+        assert r.returncode == 0 and "MLUPS" in r.stdout, r.stderr
+    else:
+        assert r.returncode == 3 and "no CPU fallback" in r.stderr
