@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
@@ -125,7 +126,7 @@ StepParams<T> make_params(lb_lattice *L)
     }
     p.n_rim_ctas = (int)((p.n_perimeter + TILE_L - 1) / TILE_L);
     p.t2_rows = L->t2_rows;
-    p.t2_tiles_l = p.lny > 4 ? (p.lny - 4 + T2_W - 1) / T2_W : 0;
+    p.t2_tiles_l = t2_tiles_over(p.lny);
     p.t2_tiles_k = p.lnx > 4 ? (p.lnx - 4 + p.t2_rows - 1) / p.t2_rows : 0;
     p.sf_uw6 = (T)((1.0 / 6.0) * L->cfg.u_wall);
     p.rho_in = (T)L->cfg.rho_in;
@@ -195,11 +196,13 @@ int launch_step(lb_lattice *L, bool collide)
 template <typename T, int BC, bool EXACT>
 int launch_double_bc(lb_lattice *L, const StepParams<T> &p, int phases = 7)
 {
-    static bool attr_set[64] = {};           // per device: the fused tile's shared-memory ring exceeds the 48 KB default
-    const int dev = L->cfg.device & 63;
-    if (!attr_set[dev]) {
+    // The fused tile's shared memory exceeds the 48 KB default.  Per device and per instantiation; the call is
+    // idempotent, so two host threads racing on the bit mask at worst both make it.
+    static std::atomic<unsigned long long> attr_done{0ull};
+    const unsigned long long dev_bit = 1ull << (L->cfg.device & 63);
+    if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
         LBM_CUDA(cudaFuncSetAttribute(t2_interior_kernel<T, BC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2_smem_bytes<T>()));
-        attr_set[dev] = true;
+        attr_done.fetch_or(dev_bit, std::memory_order_release);
     }
     const int g1 = (int)((ring_cells(p.lnx, p.lny, FRAME_W) + TILE_L - 1) / TILE_L);
     const int g3 = (int)((ring_cells(p.lnx, p.lny, 2) + TILE_L - 1) / TILE_L);
@@ -265,7 +268,7 @@ bool temporal_ok(const lb_lattice *L)
     const bool eligible = L->cfg.boundary <= LB_CAVITY_XPERIODIC && L->cfg.lnx >= 16 && L->cfg.lny >= 16 && !L->d_series;
     if (!eligible) return false;
     if (L->temporal == 2) return true;
-    const long long tiles = ((L->cfg.lny - 4 + T2_W - 1) / T2_W) * ((L->cfg.lnx - 4 + L->t2_rows - 1) / L->t2_rows);
+    const long long tiles = (long long)t2_tiles_over(L->cfg.lny) * ((L->cfg.lnx - 4 + L->t2_rows - 1) / L->t2_rows);
     return tiles >= T2_AUTO_MIN_TILES;
 }
 
@@ -358,7 +361,6 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     L->total_bytes = L->state_off + 256;
     cudaError_t e = cudaMalloc(&L->base, L->total_bytes);
     if (e != cudaSuccess) {
-        delete L;
         const size_t want = L->total_bytes;
         delete L;
         cudaGetLastError();
@@ -592,7 +594,11 @@ int lb_init_equilibrium(lb_lattice *L, const void *rho, const void *ux, const vo
     LBM_ON_DEVICE(L);
     const long long n = L->cfg.lnx * L->cfg.lny;
     const size_t bytes = (size_t)n * L->elem;
-    void *d[3] = {nullptr, nullptr, nullptr};
+    struct Tmp {      // freed on every return path
+        void *d[3] = {nullptr, nullptr, nullptr};
+        ~Tmp() { for (void *q : d) if (q) cudaFree(q); }
+    } tmp;
+    void **d = tmp.d;
     const void *h[3] = {rho, ux, uy};
     for (int j = 0; j < 3; ++j)
         if (h[j]) {
@@ -605,8 +611,6 @@ int lb_init_equilibrium(lb_lattice *L, const void *rho, const void *ux, const vo
         init_equilibrium_kernel<float><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<float>(L), (const float *)d[0], (const float *)d[1], (const float *)d[2]);
     LBM_CUDA(cudaGetLastError());
     LBM_CUDA(cudaStreamSynchronize(L->stream));
-    for (int j = 0; j < 3; ++j)
-        if (d[j]) cudaFree(d[j]);
     L->launches++;
     return 0;
 }

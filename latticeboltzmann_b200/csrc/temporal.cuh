@@ -33,26 +33,55 @@ namespace lbm {
 #define LBM_T2_TILE 256
 #endif
 constexpr int T2_TILE = LBM_T2_TILE;  // threads (= level-(n+1) columns incl. the one-cell halo) per fused tile
-constexpr int T2_W = T2_TILE - 2;     // level-(n+2) output columns per fused tile
-#ifndef LBM_T2_SLOTS
-#define LBM_T2_SLOTS 4
+// Column mapping of a fused tile: tile lt emits the level-(n+2) columns [max(2, T2_W*lt + T2_S), T2_W*(lt+1) + T2_S)
+// and thread t works on column T2_W*lt + T2_S - T2_OFF + t (level n+1 on threads T2_OFF-1 .. T2_OFF+T2_W).
+//   (254, 2, 1): every thread busy, but tile seams fall 16 B into a 32-byte sector on every other tile;
+//   (252, 0, 2): every tile's stores start on a sector boundary (252 * 8 B = 63 sectors), 2 idle lanes.
+#ifndef LBM_T2_W
+#define LBM_T2_W 254
 #endif
-// Measured at 16384^2 fp64 EXACT (GLUPS): all 9 populations through the ring, 3 CTAs/SM: 61.5; six-population
-// ring + register-kept rest/E/W with row prefetch at 80 registers / 3 CTAs: 58.8; the same WITHOUT prefetch at
-// 64 registers / 4 CTAs (32 warps): 78.1; 128-thread tiles: 60-61.  Occupancy, not prefetch depth, is what
-// hides the latency of the two collisions per row.
-#ifndef LBM_T2_PREFETCH
-#define LBM_T2_PREFETCH 0
+#ifndef LBM_T2_S
+#define LBM_T2_S 2
+#endif
+#ifndef LBM_T2_OFF
+#define LBM_T2_OFF 1
+#endif
+constexpr int T2_W = LBM_T2_W, T2_S = LBM_T2_S, T2_OFF = LBM_T2_OFF;
+static_assert(T2_OFF >= 1 && T2_OFF + T2_W <= T2_TILE - 1, "level-(n+1) halo columns must fit the tile");
+static_assert(T2_S == 0 || T2_S == 2, "tiles start at column 2 (the frame) or on multiples of T2_W");
+__host__ __device__ inline int t2_tiles_over(long long lny) { return lny > 4 ? (int)((lny - 2 - T2_S + T2_W - 1) / T2_W) : 0; }
+// Measured at 16384^2 fp64 EXACT (GLUPS), round 1: all 9 populations through the ring, 3 CTAs/SM: 61.5; six-population
+// ring + register-kept rest/E/W with register prefetch of the next row at 80 registers / 3 CTAs: 58.8; the same
+// WITHOUT prefetch at 64 registers / 4 CTAs (32 warps): 78.1; 128-thread tiles: 60-61; 3-slot ring, two barriers per
+// row: 49-63.  Round 2: LBM_T2_ASYNC stages the NEXT row's nine level-n sources in shared memory with cp.async
+// (LDGSTS: no registers held while the loads are in flight), LBM_T2_COMPACT_RING keeps only the rows each ring
+// population still needs (18 instead of 24 population-rows) so that ring + stage fit 4 CTAs per SM.
+#ifndef LBM_T2_ASYNC
+#define LBM_T2_ASYNC 1
+#endif
+#ifndef LBM_T2_COMPACT_RING
+#define LBM_T2_COMPACT_RING 1
 #endif
 #ifndef LBM_T2_MINB
 #define LBM_T2_MINB 4
 #endif
-constexpr int T2_SLOTS = LBM_T2_SLOTS;   // shared-memory ring of level-(n+1) rows (4: one barrier per row; 3: two)
 
+// Shared-memory ring of level-(n+1) rows, one barrier per row.  At iteration j (row j of level n+1 has just been
+// written) the level-(n+2) pull of row j-1 reads NW,SW from row j, N,S from row j-1 and NE,SE from row j-2, while
+// a warp that is already past the barrier may be writing row j+1: NW,SW need 2 live rows, N,S 3, NE,SE 4.
+__host__ __device__ constexpr int ring_slots(int i)
+{
+    return LBM_T2_COMPACT_RING ? ((i == 6 || i == 7) ? 2 : (i == 2 || i == 4) ? 3 : 4) : 4;
+}
+// first population-row of population i in the ring (order NW, SW, N, S, NE, SE)
+__host__ __device__ constexpr int ring_base(int i)
+{
+    return i == 6 ? 0 : i == 7 ? ring_slots(6) : i == 2 ? 2 * ring_slots(6) : i == 4 ? 2 * ring_slots(6) + ring_slots(2)
+         : i == 5 ? 2 * ring_slots(6) + 2 * ring_slots(2) : 2 * ring_slots(6) + 2 * ring_slots(2) + ring_slots(5);
+}
+constexpr int T2_RING_ROWS = 2 * ring_slots(6) + 2 * ring_slots(2) + 2 * ring_slots(5);
 template <typename T>
-__host__ __device__ constexpr int t2_smem_bytes() { return T2_SLOTS * 6 * T2_TILE * (int)sizeof(T); }
-// ring slot of the six populations that shift in y (0, E, W stay in the thread's registers)
-__host__ __device__ constexpr int ring_pop(int i) { return i == 2 ? 0 : i == 4 ? 1 : i - 3; }   // N,S,NE,NW,SW,SE -> 0..5
+__host__ __device__ constexpr int t2_smem_bytes() { return (T2_RING_ROWS + (LBM_T2_ASYNC ? 9 : 0)) * T2_TILE * (int)sizeof(T); }
 
 // cells closer than w to the perimeter (needs lnx, lny >= 2w)
 __host__ __device__ inline long long ring_cells(int lnx, int lny, int w) { return 2ll * w * lny + 2ll * w * (lnx - 2 * w); }
@@ -292,11 +321,20 @@ __global__ void __launch_bounds__(TILE_L) t2_frame2_kernel(const __grid_constant
 // K2: level n -> n+2 on the deep interior.  Level-(n+1) rows stream through the tile: the six populations
 // that shift in y go through a shared-memory ring (neighbouring threads consume them), the three that do not
 // (rest, E, W: consumed by the SAME thread one row later / earlier) stay in registers.
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+template <int BYTES>
+__device__ __forceinline__ void cp_async(unsigned dst_smem, const void *src)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_smem), "l"(src), "n"(BYTES) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 template <typename T, int BC, bool EXACT>
 __global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const __grid_constant__ StepParams<T> p)
 {
     extern __shared__ __align__(16) unsigned char t2_smem_raw[];
-    T *ring = reinterpret_cast<T *>(t2_smem_raw);               // [T2_SLOTS][6][T2_TILE]
+    T *ring = reinterpret_cast<T *>(t2_smem_raw);               // [T2_RING_ROWS][T2_TILE]
     const int par = (int)*(volatile unsigned int *)&p.st->cur;
     const T *__restrict__ src = p.buf[par];
     T *__restrict__ dst = p.buf[par ^ 1];
@@ -305,48 +343,65 @@ __global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const
     const int k0 = 2 + kt * p.t2_rows;
     const int k1 = min(k0 + p.t2_rows, p.lnx - 2);
     const int t = threadIdx.x;
-    const int lc = 2 + lt * T2_W - 1 + t;                       // this thread's column (level n+1 and level n+2)
-    const bool have1 = lc <= p.lny - 2;                         // a level-(n+1) cell at distance >= 1
-    const bool have2 = t >= 1 && t <= T2_W && lc <= p.lny - 3;  // a level-(n+2) cell at distance >= 2
+    const int lc = lt * T2_W + T2_S - T2_OFF + t;               // this thread's column (level n+1 and level n+2)
+    const bool have1 = t >= T2_OFF - 1 && t <= T2_OFF + T2_W && lc >= 1 && lc <= p.lny - 2;   // a level-(n+1) cell at distance >= 1
+    const bool have2 = t >= T2_OFF && t < T2_OFF + T2_W && lc >= 2 && lc <= p.lny - 3;        // a level-(n+2) cell at distance >= 2
     const long long row_bytes = p.pitch * (long long)sizeof(T);
     const char *sp = reinterpret_cast<const char *>(src + (long long)k0 * p.pitch + (lc + PAD_L));        // row k0-1
     T *dp = dst + (long long)(k0 + 1) * p.pitch + (lc + PAD_L);                                           // row k0
     T rest_m1 = T(0), e_m1 = T(0), e_m2 = T(0);                 // level n+1: rest of row j-1, E of rows j-1 and j-2
-#if LBM_T2_PREFETCH
-    T nxt[9];
-    if (have1) interior_load<T>(p, sp, nxt);                     // row k0-1 in flight
+#if LBM_T2_ASYNC
+    // Stage of this thread's nine level-n sources for the NEXT row: written by cp.async while the current row is
+    // collided twice, read back by the SAME thread (no barrier: cp.async.wait_group covers a thread's own copies).
+    T *stage = ring + T2_RING_ROWS * T2_TILE + t;
+    const unsigned stage_s = smem_u32(stage);
+    if (have1) {
+#pragma unroll
+        for (int i = 0; i < 9; ++i) cp_async<(int)sizeof(T)>(stage_s + i * T2_TILE * (int)sizeof(T), sp + p.ld_off[i]);
+    }
+    cp_async_commit();
 #endif
+    int s3 = (k0 - 1) % 3;                                      // ring slot of row j for the 3-slot populations (j & 1, j & 3 for the others)
 #pragma unroll 1
     for (int j = k0 - 1; j <= k1; ++j) {
         sp += row_bytes;
         T f[9];
+#if LBM_T2_ASYNC
+        cp_async_wait_all();
+#endif
         if (have1) {
-#if LBM_T2_PREFETCH
+#if LBM_T2_ASYNC
 #pragma unroll
-            for (int i = 0; i < 9; ++i) f[i] = nxt[i];
-            if (j < k1) interior_load<T>(p, sp, nxt);            // next row's loads overlap this row's two collisions
+            for (int i = 0; i < 9; ++i) f[i] = stage[i * T2_TILE];
+            if (j < k1) {
+#pragma unroll
+                for (int i = 0; i < 9; ++i) cp_async<(int)sizeof(T)>(stage_s + i * T2_TILE * (int)sizeof(T), sp + p.ld_off[i]);
+            }
+            cp_async_commit();
 #else
             interior_load<T>(p, sp - row_bytes, f);
 #endif
             d2q9_collide<T, EXACT>(f, p.omega);
-            T *slot = ring + (long long)(j % T2_SLOTS) * 6 * T2_TILE + t;
-            slot[ring_pop(QN) * T2_TILE] = f[QN];
-            slot[ring_pop(QS) * T2_TILE] = f[QS];
-            slot[ring_pop(QNE) * T2_TILE] = f[QNE];
-            slot[ring_pop(QNW) * T2_TILE] = f[QNW];
-            slot[ring_pop(QSW) * T2_TILE] = f[QSW];
-            slot[ring_pop(QSE) * T2_TILE] = f[QSE];
+#define LBM_RING_W(I, SLOT) ring[(ring_base(I) + (ring_slots(I) == 2 ? (j & 1) : ring_slots(I) == 3 ? s3 : (j & 3))) * T2_TILE + t] = f[I]
+            LBM_RING_W(QN, 0);
+            LBM_RING_W(QS, 0);
+            LBM_RING_W(QNE, 0);
+            LBM_RING_W(QNW, 0);
+            LBM_RING_W(QSW, 0);
+            LBM_RING_W(QSE, 0);
+#undef LBM_RING_W
         }
         __syncthreads();
         const T rest_0 = f[Q0], e_0 = f[QE], w_0 = f[QW];       // level n+1, row j, this column
         if (j >= k0 + 1) {                                       // level-(n+1) rows j-2, j-1, j are available: emit row j-1
             if (have2) {
-                const int jo = j - 1;
                 T g[9];
-                g[Q0] = rest_m1;                                 // (jo, lc)
-                g[QE] = e_m2;                                    // pulled from row jo-1
-                g[QW] = w_0;                                     // pulled from row jo+1
-#define LBM_RING(I) ring[((long long)((jo - cx_of(I)) % T2_SLOTS) * 6 + ring_pop(I)) * T2_TILE + (t - cy_of(I))]
+                g[Q0] = rest_m1;                                 // (j-1, lc)
+                g[QE] = e_m2;                                    // pulled from row j-2
+                g[QW] = w_0;                                     // pulled from row j
+                // slot of row j - d for a population with n slots, from the running slot counters of row j
+#define LBM_SLOT(I, D) (ring_slots(I) == 2 ? ((j - (D)) & 1) : ring_slots(I) == 3 ? ((s3 + 3 - (D)) % 3) : ((j - (D)) & 3))
+#define LBM_RING(I) ring[(ring_base(I) + LBM_SLOT(I, 1 + cx_of(I))) * T2_TILE + (t - cy_of(I))]
                 g[QN] = LBM_RING(QN);
                 g[QS] = LBM_RING(QS);
                 g[QNE] = LBM_RING(QNE);
@@ -354,6 +409,7 @@ __global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const
                 g[QSW] = LBM_RING(QSW);
                 g[QSE] = LBM_RING(QSE);
 #undef LBM_RING
+#undef LBM_SLOT
                 d2q9_collide<T, EXACT>(g, p.omega);
                 T *q = dp;
 #pragma unroll
@@ -367,8 +423,11 @@ __global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const
         e_m2 = e_m1;
         e_m1 = e_0;
         rest_m1 = rest_0;
-        if (T2_SLOTS < 4) __syncthreads();                       // 3 slots: row j+1 overwrites the slot of row j-2 just read
+        s3 = s3 == 2 ? 0 : s3 + 1;
     }
+#if LBM_T2_ASYNC
+    cp_async_wait_all();
+#endif
 }
 
 }  // namespace lbm
