@@ -42,7 +42,7 @@ struct lb_lattice {
     int graph_rows_per_tile = 0;
     bool use_graph = true;
     int temporal = 0;            // 0: auto (two steps per HBM pass when the block is big enough to fill the GPU), 1: single-step kernel, 2: force temporal blocking
-    int t2_rows = 32;
+    int t2_rows = 0;             // rows per fused tile; 0: automatic (t2_rows_for)
     cudaGraphExec_t graph2_exec = nullptr;   // GRAPH_DOUBLE double steps
     cudaStream_t graph2_stream = nullptr;
     int graph2_rows = 0;
@@ -94,6 +94,10 @@ void drop_graph(lb_lattice *L)
 
 DevState *dev_state(lb_lattice *L) { return reinterpret_cast<DevState *>(L->base + L->state_off); }
 
+// Rows per fused tile.  64-row tiles recompute half as many level-(n+1) halo rows (2 per 64) but measured no
+// faster with the TMA-staged kernel (16384^2 fp64 EXACT: 87.1 vs 87.5 GLUPS), so 32 is the default.
+int t2_rows_for(const lb_lattice *L) { return L->t2_rows > 0 ? L->t2_rows : 32; }
+
 template <typename T>
 StepParams<T> make_params(lb_lattice *L)
 {
@@ -125,7 +129,7 @@ StepParams<T> make_params(lb_lattice *L)
         p.n_perimeter = (long long)p.lny + (p.lnx > 1 ? p.lny : 0) + (p.lny > 1 ? 2 : 1) * (long long)(p.lnx > 2 ? p.lnx - 2 : 0);
     }
     p.n_rim_ctas = (int)((p.n_perimeter + TILE_L - 1) / TILE_L);
-    p.t2_rows = L->t2_rows;
+    p.t2_rows = t2_rows_for(L);
     p.t2_tiles_l = t2_tiles_over(p.lny);
     p.t2_tiles_k = p.lnx > 4 ? (p.lnx - 4 + p.t2_rows - 1) / p.t2_rows : 0;
     p.sf_uw6 = (T)((1.0 / 6.0) * L->cfg.u_wall);
@@ -233,7 +237,7 @@ constexpr int GRAPH_DOUBLE = 32;     // double steps per graph launch (64 time s
 
 int ensure_graph2(lb_lattice *L)
 {
-    if (L->graph2_exec && L->graph2_stream == L->stream && L->graph2_rows == L->t2_rows) return 0;
+    if (L->graph2_exec && L->graph2_stream == L->stream && L->graph2_rows == t2_rows_for(L)) return 0;
     if (L->graph2_exec) cudaGraphExecDestroy(L->graph2_exec);
     L->graph2_exec = nullptr;
     // first launch outside the capture: it sets the kernels' shared-memory attribute
@@ -254,7 +258,7 @@ int ensure_graph2(lb_lattice *L)
         return lbm_fail(LB_ERR_CUDA, "cudaGraphInstantiate: %s", cudaGetErrorString(e));
     }
     L->graph2_stream = L->stream;
-    L->graph2_rows = L->t2_rows;
+    L->graph2_rows = t2_rows_for(L);
     return 0;
 }
 
@@ -268,7 +272,7 @@ bool temporal_ok(const lb_lattice *L)
     const bool eligible = L->cfg.boundary <= LB_CAVITY_XPERIODIC && L->cfg.lnx >= 16 && L->cfg.lny >= 16 && !L->d_series;
     if (!eligible) return false;
     if (L->temporal == 2) return true;
-    const long long tiles = (long long)t2_tiles_over(L->cfg.lny) * ((L->cfg.lnx - 4 + L->t2_rows - 1) / L->t2_rows);
+    const long long tiles = (long long)t2_tiles_over(L->cfg.lny) * ((L->cfg.lnx - 4 + 31) / 32);     // counted in 32-row tiles (decomposition.py)
     return tiles >= T2_AUTO_MIN_TILES;
 }
 

@@ -53,17 +53,32 @@ __host__ __device__ inline int t2_tiles_over(long long lny) { return lny > 4 ? (
 // Measured at 16384^2 fp64 EXACT (GLUPS), round 1: all 9 populations through the ring, 3 CTAs/SM: 61.5; six-population
 // ring + register-kept rest/E/W with register prefetch of the next row at 80 registers / 3 CTAs: 58.8; the same
 // WITHOUT prefetch at 64 registers / 4 CTAs (32 warps): 78.1; 128-thread tiles: 60-61; 3-slot ring, two barriers per
-// row: 49-63.  Round 2: LBM_T2_ASYNC stages the NEXT row's nine level-n sources in shared memory with cp.async
-// (LDGSTS: no registers held while the loads are in flight), LBM_T2_COMPACT_RING keeps only the rows each ring
-// population still needs (18 instead of 24 population-rows) so that ring + stage fit 4 CTAs per SM.
+// row: 49-63.  Round 2 (tools/t2_variants.py, profiles/r02_t2_variants.log): LBM_T2_COMPACT_RING keeps only the rows
+// each ring population still needs (18 instead of 24 population-rows): 78.6 -> 80.3 (32-row tiles) / 80.8 (64-row
+// tiles); LBM_T2_ASYNC stages the NEXT row's nine level-n sources with per-thread 8-byte cp.async (LDGSTS): 60.6 --
+// the LSU/MIO path of 9 x 8-byte LDGSTS per cell costs more than the latency it hides (ncu: mio_throttle 5.6 per
+// issue), so it stays off; sector-aligned tile seams (W=252): 78.4, no gain.
 #ifndef LBM_T2_ASYNC
-#define LBM_T2_ASYNC 1
+#define LBM_T2_ASYNC 0
 #endif
 #ifndef LBM_T2_COMPACT_RING
 #define LBM_T2_COMPACT_RING 1
 #endif
 #ifndef LBM_T2_MINB
-#define LBM_T2_MINB 4
+#define LBM_T2_MINB 2
+#endif
+// LBM_T2_TMA: the nine level-n source segments of a row (258 contiguous elements each, 16-byte aligned supersets of
+// the 256 a tile needs) are staged in shared memory by bulk-async copies (cp.async.bulk, SASS UBLKCP) that ONE
+// thread issues LBM_T2_STAGES rows ahead and an mbarrier per stage completes: the loads are in flight while the
+// CTA's warps collide, without holding registers and without per-thread LDGSTS traffic.  Measured at 16384^2 fp64
+// EXACT, 32-row tiles (GLUPS; profiles/r02_t2_variants.log): direct loads, compact ring, 4 CTAs/SM 80.1; TMA 1 stage
+// x 4 CTAs/SM 84.0; 2 stages x 3 CTAs 85.1; 3 stages x 2 CTAs 87.5 (shipped: 6.30 TB/s of pass traffic = 0.963 of the
+// measured copy peak); 4 stages x 2 CTAs 87.5.  Prefetch depth, not occupancy, hides the DRAM latency here.
+#ifndef LBM_T2_TMA
+#define LBM_T2_TMA 1
+#endif
+#ifndef LBM_T2_STAGES
+#define LBM_T2_STAGES 3
 #endif
 
 // Shared-memory ring of level-(n+1) rows, one barrier per row.  At iteration j (row j of level n+1 has just been
@@ -81,7 +96,13 @@ __host__ __device__ constexpr int ring_base(int i)
 }
 constexpr int T2_RING_ROWS = 2 * ring_slots(6) + 2 * ring_slots(2) + 2 * ring_slots(5);
 template <typename T>
-__host__ __device__ constexpr int t2_smem_bytes() { return (T2_RING_ROWS + (LBM_T2_ASYNC ? 9 : 0)) * T2_TILE * (int)sizeof(T); }
+__host__ __device__ constexpr int t2_seg_elems() { return T2_TILE + 16 / (int)sizeof(T); }   // staged segment: tile + one 16-byte unit
+template <typename T>
+__host__ __device__ constexpr int t2_smem_bytes()
+{
+    return (T2_RING_ROWS + (LBM_T2_ASYNC ? 9 : 0)) * T2_TILE * (int)sizeof(T) +
+           (LBM_T2_TMA ? LBM_T2_STAGES * (9 * t2_seg_elems<T>() * (int)sizeof(T) + 16) : 0);
+}
 
 // cells closer than w to the perimeter (needs lnx, lny >= 2w)
 __host__ __device__ inline long long ring_cells(int lnx, int lny, int w) { return 2ll * w * lny + 2ll * w * (lnx - 2 * w); }
@@ -330,10 +351,38 @@ __device__ __forceinline__ void cp_async(unsigned dst_smem, const void *src)
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 
+// mbarrier + bulk-async copy (TMA unit, no tensor map: plain 1-D copies)
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned bar, unsigned bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+    unsigned done;
+    do {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+            "selp.u32 %0, 1, 0, p;\n"
+            "}\n" : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+    } while (!done);
+}
+__device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src, unsigned bytes, unsigned bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(dst_smem), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
 template <typename T, int BC, bool EXACT>
 __global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const __grid_constant__ StepParams<T> p)
 {
-    extern __shared__ __align__(16) unsigned char t2_smem_raw[];
+    extern __shared__ __align__(128) unsigned char t2_smem_raw[];
     T *ring = reinterpret_cast<T *>(t2_smem_raw);               // [T2_RING_ROWS][T2_TILE]
     const int par = (int)*(volatile unsigned int *)&p.st->cur;
     const T *__restrict__ src = p.buf[par];
@@ -361,6 +410,35 @@ __global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const
     }
     cp_async_commit();
 #endif
+#if LBM_T2_TMA
+    constexpr int AL = 16 / (int)sizeof(T), SEG = t2_seg_elems<T>(), NST = LBM_T2_STAGES;
+    const T *stage = ring + T2_RING_ROWS * T2_TILE;             // [NST][9][SEG]
+    const unsigned stage_s = smem_u32(stage);
+    const unsigned full_s = stage_s + NST * 9 * SEG * (unsigned)sizeof(T);   // NST mbarriers, 8 bytes each
+    const int lc0 = lt * T2_W + T2_S - T2_OFF;                  // column of thread 0
+    // stage `st` <- the nine source segments of level-(n+1) row `row`: population i from row (row - cx_i), columns
+    // from (lc0 - cy_i) rounded down to a 16-byte unit
+    auto stage_row = [&](int row, int st) {
+        mbar_expect_tx(full_s + 8u * st, 9u * SEG * (unsigned)sizeof(T));
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const T *g = src + (long long)i * p.pop_stride + (long long)(row - cx_of(i) + 1) * p.pitch + (PAD_L + (((lc0 - cy_of(i)) / AL) * AL));
+            bulk_g2s(stage_s + (unsigned)((st * 9 + i) * SEG * (int)sizeof(T)), g, SEG * (unsigned)sizeof(T), full_s + 8u * st);
+        }
+    };
+    if (t == 0) {
+#pragma unroll
+        for (int st = 0; st < NST; ++st) mbar_init(full_s + 8u * st, 1u);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        fence_proxy_async();
+#pragma unroll
+        for (int st = 0; st < NST; ++st)
+            if (k0 - 1 + st <= k1) stage_row(k0 - 1 + st, st);
+    }
+    __syncthreads();
+    int st_cur = 0;
+    unsigned st_par = 0u;
+#endif
     int s3 = (k0 - 1) % 3;                                      // ring slot of row j for the 3-slot populations (j & 1, j & 3 for the others)
 #pragma unroll 1
     for (int j = k0 - 1; j <= k1; ++j) {
@@ -369,8 +447,14 @@ __global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const
 #if LBM_T2_ASYNC
         cp_async_wait_all();
 #endif
+#if LBM_T2_TMA
+        mbar_wait(full_s + 8u * st_cur, st_par);
+#endif
         if (have1) {
-#if LBM_T2_ASYNC
+#if LBM_T2_TMA
+#pragma unroll
+            for (int i = 0; i < 9; ++i) f[i] = stage[(st_cur * 9 + i) * SEG + ((lc0 - cy_of(i)) & (AL - 1)) + t];
+#elif LBM_T2_ASYNC
 #pragma unroll
             for (int i = 0; i < 9; ++i) f[i] = stage[i * T2_TILE];
             if (j < k1) {
@@ -392,6 +476,14 @@ __global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const
 #undef LBM_RING_W
         }
         __syncthreads();
+#if LBM_T2_TMA
+        // every thread has read stage st_cur (before the barrier): refill it with the row NST iterations ahead
+        if (t == 0 && j + NST <= k1) {
+            fence_proxy_async();
+            stage_row(j + NST, st_cur);
+        }
+        if (++st_cur == NST) { st_cur = 0; st_par ^= 1u; }
+#endif
         const T rest_0 = f[Q0], e_0 = f[QE], w_0 = f[QW];       // level n+1, row j, this column
         if (j >= k0 + 1) {                                       // level-(n+1) rows j-2, j-1, j are available: emit row j-1
             if (have2) {

@@ -14,7 +14,11 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "latticeboltzmann_b200", "csrc", "variants")
 
 VARIANTS = {
-    "r1": ["LBM_T2_ASYNC=0", "LBM_T2_COMPACT_RING=0"],                                  # round-1 shipped kernel
+    "tma1": ["LBM_T2_TMA=1", "LBM_T2_STAGES=1", "LBM_T2_MINB=4"],
+    "tma2": ["LBM_T2_TMA=1", "LBM_T2_STAGES=2", "LBM_T2_MINB=3"],
+    "tma4": ["LBM_T2_TMA=1", "LBM_T2_STAGES=4", "LBM_T2_MINB=2"],
+    "tma3": ["LBM_T2_TMA=1", "LBM_T2_STAGES=3", "LBM_T2_MINB=2"],
+    "r1": ["LBM_T2_ASYNC=0", "LBM_T2_COMPACT_RING=0"],                                 # round-1 shipped kernel
     "compact": ["LBM_T2_ASYNC=0", "LBM_T2_COMPACT_RING=1"],
     "async4": ["LBM_T2_ASYNC=1", "LBM_T2_COMPACT_RING=1", "LBM_T2_MINB=4"],
     "async3": ["LBM_T2_ASYNC=1", "LBM_T2_COMPACT_RING=0", "LBM_T2_MINB=3"],
