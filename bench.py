@@ -125,8 +125,8 @@ def measured_hbm_peak():
 
 def ncu_traffic_per_launch(arith, cells):
     """dram__bytes_read.sum + dram__bytes_write.sum per step-kernel launch from the committed ncu
-    captures (profiles/r01_step_kernel_dram.json: one entry per arith x cells-per-launch), or None."""
-    p = os.path.join(ROOT, "profiles", "r01_step_kernel_dram.json")
+    captures (profiles/r02_kernel_dram.json: one entry per arith x cells-per-launch), or None."""
+    p = os.path.join(ROOT, "profiles", "r02_kernel_dram.json")
     try:
         with open(p) as fh:
             for e in json.load(fh)["captures"]:
@@ -155,7 +155,9 @@ def cpu_reference(nx_total, ny_total, omega, steps, warmup, cores=None):
     t = opt2_numpy.run_independent_blocks(p, bx, by, omega, warmup, steps)
     mlups = p * bx * by * steps / t / 1e6
     cpu_reference.last_ms_per_step = t / steps * 1e3
-    desc = "%d processes x %dx%d single-rank opt2 blocks (np.roll stream + numpy walls + compiled collide), %d steps" % (p, bx, by, steps)
+    desc = ("%d processes x %dx%d single-rank opt2 blocks = %d cells sampled of the %d-cell workload, %d steps; each block is "
+            "stepped like the reference (np.roll stream + numpy walls + compiled collide) but WITHOUT halo exchange between "
+            "the blocks (mpirun / mpi4py are not installed)" % (p, bx, by, p * bx * by, nx_total * ny_total, steps))
     return mlups, p, desc
 
 
@@ -165,7 +167,7 @@ def run_reference_arm(args):
         return
     nx, ny, ndx, ndy, scaling, desc = workload(args.workload, args.gpus)
     omega = omega_for_re(nx)
-    steps = max(1, min(args.steps, 10))
+    steps = max(1, min(args.steps, 50))       # ~0.3 s per step on 16 cores: the requested count whenever it fits a minute
     mlups, cores, sample = cpu_reference(nx, ny, omega, steps, max(1, min(args.warmup, 2)))
     ms = cpu_reference.last_ms_per_step
     line = {"impl": "reference", "metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus,
@@ -213,6 +215,66 @@ def e2e_host_step(lat, steps):
     return dt / steps, host.numel() * 8
 
 
+def parity_selfcheck(D, ndx, ndy, device):
+    """Before anything is timed: the deterministic ragged cases of latticeboltzmann_b200/selfcheck.py through the
+    SAME decomposition and halo path as the benchmark (forced temporal blocking, odd step count => double steps +
+    one single step), gathered and compared by SHA-256 with the CPU oracle's result committed under
+    tests/golden/bench_parity.json (tests/make_bench_parity.py).  The oracle itself is not imported here."""
+    import torch.distributed as dist
+    from latticeboltzmann_b200 import selfcheck
+    with open(os.path.join(ROOT, "tests", "golden", "bench_parity.json")) as fh:
+        golden = json.load(fh)["sha256"]
+    out = {"bit_exact": True, "ndx": ndx, "ndy": ndy, "cases": {},
+           "golden": "tests/golden/bench_parity.json (CPU oracle, tests/make_bench_parity.py)"}
+    for name, (boundary, nx, ny, dtype, omega, u0, steps) in selfcheck.CASES.items():
+        lat = D.DistributedLattice(nx, ny, ndx, ndy, boundary, omega=omega, u_wall=u0, dtype=np.dtype(dtype),
+                                   arith="exact", device=device, temporal=2)
+        b = lat.blockinfo
+        lat.init_equilibrium(*selfcheck.fields(nx, ny, dtype, b.x0, b.y0, b.lnx, b.lny))
+        t2 = lat.block.temporal_active
+        lat.step(steps)
+        g = lat.gather_f(0)
+        lat.health()
+        lat.close()
+        if dist.get_rank() == 0:
+            ok = selfcheck.digest(g) == golden[name]
+            out["cases"][name] = {"bit_exact": ok, "temporal_blocking": bool(t2), "steps": steps}
+            out["bit_exact"] = out["bit_exact"] and ok
+    return out
+
+
+def timed_lattice(D, nx, ny, ndx, ndy, omega, dtype, arith, device, temporal, warmup, steps, rows_per_tile=None):
+    """init -> warmup -> `steps` timed steps (barrier + sync, CUDA events, max over ranks) -> digest.  Returns
+    (lattice still open, ms, global digest after warmup + steps)."""
+    lat = D.DistributedLattice(nx, ny, ndx, ndy, "cavity", omega=omega, u_wall=0.1, dtype=dtype, arith=arith,
+                               device=device, rows_per_tile=rows_per_tile, temporal=temporal)
+    lat.init_equilibrium()
+    lat.step(warmup)
+    lat.sync()
+    ms = lat.step_timed(steps)
+    lat.health()
+    return lat, ms, lat.checksum()
+
+
+def strip_rows(lnx, rows=64):
+    """A strip of `rows` rows in the middle of the block that straddles two row seams of the fused tiles
+    (tiles start at row 2 + 32 m)."""
+    a = 2 + 32 * max(1, lnx // 64) - 16
+    return (a, a + rows) if a - 2 >= 0 and a + rows + 2 <= lnx else None
+
+
+def strip_check_vs_oracle(pre, post, omega, u0):
+    """cpu_baseline leg only (the one place bench.py may run oracle/): two oracle steps on the downloaded strip
+    `pre` (rows a-2 .. a+rows+2, all columns, level n) must reproduce `post` (rows a .. a+rows, level n+2)
+    bit for bit.  The strip is interior in x, so the oracle runs it without left/right walls; its wrapped edge
+    rows are garbage after each step and are not compared."""
+    from oracle import oracle as orc
+    t1, t2 = np.empty_like(pre), np.empty_like(pre)
+    orc.cavity_step_pull(pre, t1, omega, u0=u0, walls_lr=False)
+    orc.cavity_step_pull(t1, t2, omega, u0=u0, walls_lr=False)
+    return bool(np.array_equal(t2[:, 2:-2], post))
+
+
 _REAL_STDOUT = None
 
 
@@ -248,6 +310,7 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the parity self-check, the single-step comparison and the extra workloads (profiling runs)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3
@@ -265,6 +328,10 @@ def main():
         raise SystemExit("--gpus %d but WORLD_SIZE=%d (launch with torch.distributed.run for N > 1)" % (args.gpus, world))
     rank, world, local_rank = D.init_process_group("nccl")
     numa = D.bind_to_gpu_numa(local_rank) if world > 1 else None      # pinned e2e buffers next to their GPU
+
+    # ---- parity first: ragged lattices through this decomposition, against the committed oracle hashes --------
+    parity = None if args.no_extras else parity_selfcheck(D, ndx, ndy, local_rank)
+
     lat = D.DistributedLattice(nx, ny, ndx, ndy, "cavity", omega=omega, u_wall=0.1, dtype=np.float64,
                                arith=args.arith, device=local_rank, rows_per_tile=args.rows_per_tile or None,
                                temporal=args.temporal)
@@ -283,6 +350,7 @@ def main():
     launches = lat.block.kernel_launches - launches0
     clocks = sampler.stop(t0, t1) if rank == 0 else None
     lat.health()
+    digest_main = None if args.no_extras else lat.checksum()     # global state after warmup + steps (device-side digest)
 
     cells = nx * ny
     mlups = cells * args.steps / (ms * 1e-3) / 1e6
@@ -298,6 +366,17 @@ def main():
     achieved = b.lnx * b.lny * BYTES_PER_CELL / (per_pass_ms * 1e-3) / 1e9
     peak, peak_src = measured_hbm_peak()
     traffic = ncu_traffic_per_launch(args.arith + ("+t2" if t2 else ""), b.lnx * b.lny)
+
+    # Strip of the benchmarked state for the oracle (checked in the cpu_baseline leg below): level n rows with a
+    # two-row halo, one more pass of the stepping kernel, level n+2 rows.
+    strip = None
+    if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline and not args.no_extras:
+        rows = strip_rows(b.lnx)
+        if rows:
+            pre = lat.block.download_rows(rows[0] - 2, rows[1] + 2)
+            lat.step(2)
+            lat.sync()
+            strip = (rows, pre, lat.block.download_rows(rows[0], rows[1]))
 
     e2e = None
     need = 9 * b.lnx * b.lny * 8 * world
@@ -316,6 +395,51 @@ def main():
                             "lb_upload_f + lb_halo_refresh + lb_step(1) + lb_download_f on pinned host f[9,lnx,lny] per rank; bytes are per rank")}
         except Exception as exc:      # reported, never hidden
             e2e = {"value": None, "unit": "MLUPS", "error": repr(exc)}
+    lat.close()
+
+    # ---- the stated metric: the SINGLE-STEP kernel (144 B per cell per step) on the same workload, same step
+    # count; its final state must have the same digest as the temporal-blocking run (two steps per pass ==
+    # single steps, bit for bit, at the benchmarked size).
+    single = None
+    extra = {}
+    free_b = torch.cuda.mem_get_info(local_rank)[0]
+    lattice_b = 2 * 9 * (b.lnx + 2) * (b.lny + 64) * 8
+    if not args.no_extras and t2:
+        if lattice_b * 1.02 < free_b:
+            lat1, ms1, digest1 = timed_lattice(D, nx, ny, ndx, ndy, omega, np.float64, args.arith, local_rank, 1,
+                                               args.warmup, args.steps, args.rows_per_tile or None)
+            lat1.close()
+            gbs1 = b.lnx * b.lny * BYTES_PER_CELL / (ms1 / args.steps * 1e-3) / 1e9
+            single = {"value": cells * args.steps / (ms1 * 1e-3) / 1e6, "unit": "MLUPS", "ms_per_step": ms1 / args.steps,
+                      "achieved_gbs": gbs1, "frac": gbs1 / peak, "kernel": "step_kernel (one pass over HBM per step, 144 B per cell per step)",
+                      "same_state_as_temporal_blocking": digest1 == digest_main, "digest": "%016x" % digest1}
+        else:
+            single = {"value": None, "skipped": "a second %.0f GB lattice does not fit next to nothing: %.0f GB free" % (lattice_b / 1e9, free_b / 1e9)}
+
+    # ---- extras: the other BASELINE.json configurations in the same invocation (so SCALE records them) ---------
+    if not args.no_extras and args.workload == "weak16384":
+        try:
+            # configs[3]: strong scaling, 32768^2 over N x-slabs (one GPU holds it in 155 GB).  The digest is a
+            # function of the GLOBAL field only, so equal digests at N = 1, 2, 4, 8 mean bit-identical fields.
+            sn = 32768
+            latS, msS, digS = timed_lattice(D, sn, sn, args.gpus, 1, omega_for_re(sn), np.float64, args.arith, local_rank, 2, 4, 12)
+            bS = latS.blockinfo
+            latS.close()
+            gbsS = bS.lnx * bS.lny * BYTES_PER_CELL / (msS / 6 * 1e-3) / 1e9
+            extra["strong32768"] = {"value": sn * sn * 12 / (msS * 1e-3) / 1e6, "unit": "MLUPS", "ms_per_step": msS / 12, "steps": 12,
+                                    "warmup": 4, "blocks": "%dx1 x-slabs" % args.gpus, "achieved_gbs_per_gpu": gbsS, "frac": gbsS / peak,
+                                    "digest_after_16_steps": "%016x" % digS,
+                                    "note": "the digest depends on the global field only: equal at N=1,2,4,8 <=> bit-identical fields"}
+        except Exception as exc:
+            extra["strong32768"] = {"value": None, "error": repr(exc)}
+        try:
+            latF, msF, _ = timed_lattice(D, nx, ny, ndx, ndy, omega, np.float32, args.arith, local_rank, 2, args.warmup, args.steps)
+            latF.close()
+            gbsF = b.lnx * b.lny * 72 / (msF / (args.steps / 2) * 1e-3) / 1e9
+            extra["fp32_temporal_blocking"] = {"value": cells * args.steps / (msF * 1e-3) / 1e6, "unit": "MLUPS", "ms_per_step": msF / args.steps,
+                                               "achieved_gbs": gbsF, "frac": gbsF / peak, "bytes_per_cell_per_pass": 72}
+        except Exception as exc:
+            extra["fp32_temporal_blocking"] = {"value": None, "error": repr(exc)}
 
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
@@ -327,8 +451,18 @@ def main():
                "one_core_value": cap * cap * 2 / one / 1e6,
                "note": "value: reference-structured opt2 step (np.roll stream + numpy walls + compiled collide) on all cores used; "
                        "one_core_value: the same on 1 core"}
+        if strip:
+            rows, pre, post = strip
+            ok = strip_check_vs_oracle(pre, post, omega, 0.1)
+            if parity is not None:
+                parity["benchmarked_state_strip"] = {
+                    "bit_exact": ok, "rows": list(rows), "columns": "all %d" % b.lny, "steps": 2,
+                    "what": "rows of the %dx%d state after the timed region advanced one more pass on the GPU == two oracle steps on the downloaded strip" % (nx, ny)}
+                parity["bit_exact"] = parity["bit_exact"] and ok
+    if parity is not None and single and single.get("value"):
+        parity["two_steps_per_pass_equals_single_steps_at_full_size"] = single["same_state_as_temporal_blocking"]
+        parity["bit_exact"] = parity["bit_exact"] and single["same_state_as_temporal_blocking"]
 
-    lat.close()
     if rank == 0:
         line = {"metric": METRIC, "value": mlups, "unit": "MLUPS", "n_gpus": args.gpus, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": scaling,
@@ -344,9 +478,14 @@ def main():
                              "traffic": (traffic or {}).get("dram_bytes_per_launch"), "peak_source": peak_src,
                              "bytes_per_cell_per_pass": BYTES_PER_CELL, "steps_per_pass": steps_per_pass,
                              "cells_per_launch": b.lnx * b.lny, "ms_per_pass": per_pass_ms,
+                             "frac_per_step_144B": mlups / world * 1e6 * BYTES_PER_CELL / 1e9 / peak,
+                             "frac_per_step_144B_note": ("MLUPS per GPU x 144 B / peak, BASELINE's definition: above 1 because temporal blocking moves "
+                                                         "144 B per cell per TWO steps; `frac` is per pass (bytes really moved)" if t2 else
+                                                         "one pass per step: equals frac"),
                              "kernel": "t2_interior_kernel (+ 2 frame kernels per pass)" if t2 else "step_kernel",
                              "traffic_note": (traffic or {}).get("note")},
-                "cpu_baseline": cpu}
+                "single_step": single, "parity": parity, "state_digest": ("%016x" % digest_main) if digest_main is not None else None,
+                "extra": extra, "cpu_baseline": cpu}
         emit(line)
     import torch.distributed as dist
     if dist.is_initialized():

@@ -143,6 +143,17 @@ LB_API int lb_halo_refresh(lb_lattice *lat);
  * f_ikl layout (cavity_opt2.py:79-83), ghosts excluded.                        */
 LB_API int lb_upload_f(lb_lattice *lat, const void *host_f);
 LB_API int lb_download_f(lb_lattice *lat, void *host_f);
+/* Rows [k_lo, k_hi) of the current state to / from a C-contiguous host array (9, k_hi - k_lo, lny): strip
+ * checks against the oracle at sizes whose full field does not fit a host, block-wise checkpoints.
+ * After lb_upload_rows the caller refreshes the halos (lb_halo_refresh) like after lb_upload_f.        */
+LB_API int lb_download_rows(lb_lattice *lat, int64_t k_lo, int64_t k_hi, void *host_rows);
+LB_API int lb_upload_rows(lb_lattice *lat, int64_t k_lo, int64_t k_hi, const void *host_rows);
+/* 64-bit digest of the current state, computed on the device: sum over populations and real cells of
+ * mix(bit pattern, GLOBAL cell index) modulo 2^64.  The digests of the blocks of ANY decomposition add up
+ * (mod 2^64) to the digest of the undecomposed lattice, so "1 GPU == N GPUs" and "two steps per pass ==
+ * single steps" can be checked bit for bit at sizes that are never gathered (cavity_opt2.py has no
+ * counterpart; the gate is BASELINE.json's bit-exact decomposition requirement).                       */
+LB_API int lb_checksum(lb_lattice *lat, uint64_t *digest);
 /* f = feq(rho, ux, uy) with the arithmetic of c/d2q9.h:59-81 (cavity_opt2.py:265-269).
  * Host arrays of lnx*lny values, or NULL for rho = 1 / u = 0.                  */
 LB_API int lb_init_equilibrium(lb_lattice *lat, const void *rho, const void *ux, const void *uy);

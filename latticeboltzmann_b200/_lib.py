@@ -60,6 +60,9 @@ SYMBOLS = {
     "lb_halo_refresh": (ctypes.c_int, [c_vp]),
     "lb_upload_f": (ctypes.c_int, [c_vp, c_vp]),
     "lb_download_f": (ctypes.c_int, [c_vp, c_vp]),
+    "lb_download_rows": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp]),
+    "lb_upload_rows": (ctypes.c_int, [c_vp, c_i64, c_i64, c_vp]),
+    "lb_checksum": (ctypes.c_int, [c_vp, _P(ctypes.c_uint64)]),
     "lb_init_equilibrium": (ctypes.c_int, [c_vp, c_vp, c_vp, c_vp]),
     "lb_step": (ctypes.c_int, [c_vp, c_i64]),
     "lb_stream_only": (ctypes.c_int, [c_vp, c_i64]),

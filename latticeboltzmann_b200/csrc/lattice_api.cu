@@ -757,14 +757,17 @@ int launch_rows(lb_lattice *L, const StepParams<T> &p, int k_lo, int k_hi)
     return 0;
 }
 
-// rows [k_lo, k_hi) of all 9 populations between the host array (9, lnx, lny) and buffer `par`
-int copy_rows(lb_lattice *L, void *host, int par, int64_t k_lo, int64_t k_hi, bool upload, cudaStream_t st)
+// rows [k_lo, k_hi) of all 9 populations between buffer `par` and a host array (9, hrows, lny) whose first row
+// is lattice row hk0 (the whole block by default: hk0 = 0, hrows = lnx)
+int copy_rows(lb_lattice *L, void *host, int par, int64_t k_lo, int64_t k_hi, bool upload, cudaStream_t st,
+              int64_t hk0 = 0, int64_t hrows = -1)
 {
     const size_t e = L->elem, row = (size_t)L->cfg.lny * e;
+    if (hrows < 0) hrows = L->cfg.lnx;
     char *buf = L->base + (size_t)par * L->buf_bytes;
     for (int i = 0; i < 9; ++i) {
         char *d = buf + ((size_t)i * L->pop_stride + (size_t)(k_lo + 1) * L->pitch + PAD_L) * e;
-        char *h = static_cast<char *>(host) + ((size_t)i * L->cfg.lnx + (size_t)k_lo) * row;
+        char *h = static_cast<char *>(host) + ((size_t)i * hrows + (size_t)(k_lo - hk0)) * row;
         if (upload)
             LBM_CUDA(cudaMemcpy2DAsync(d, (size_t)L->pitch * e, h, row, row, (size_t)(k_hi - k_lo), cudaMemcpyHostToDevice, st));
         else
@@ -927,6 +930,44 @@ int lb_probe_shear_read(lb_lattice *L, void *out, int64_t n)
     LBM_ON_DEVICE(L);
     LBM_CUDA(cudaStreamSynchronize(L->stream));
     LBM_CUDA(cudaMemcpy(out, L->d_series, (size_t)n * L->elem, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+/* Rows [k_lo, k_hi) of the current state to / from a C-contiguous host array (9, k_hi - k_lo, lny). */
+static int rows_io(lb_lattice *L, int64_t k_lo, int64_t k_hi, void *host, bool upload)
+{
+    if (!L || !host) return lbm_fail(LB_ERR_INVALID, "null argument");
+    if (k_lo < 0 || k_hi > L->cfg.lnx || k_lo >= k_hi) return lbm_fail(LB_ERR_INVALID, "row range [%lld, %lld) outside the block", (long long)k_lo, (long long)k_hi);
+    LBM_ON_DEVICE(L);
+    if (int r = copy_rows(L, host, L->cur, k_lo, k_hi, upload, L->stream, k_lo, k_hi - k_lo)) return r;
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    return 0;
+}
+int lb_download_rows(lb_lattice *L, int64_t k_lo, int64_t k_hi, void *host) { return rows_io(L, k_lo, k_hi, host, false); }
+int lb_upload_rows(lb_lattice *L, int64_t k_lo, int64_t k_hi, const void *host) { return rows_io(L, k_lo, k_hi, const_cast<void *>(host), true); }
+
+int lb_checksum(lb_lattice *L, uint64_t *out)
+{
+    if (!L || !out) return lbm_fail(LB_ERR_INVALID, "null argument");
+    LBM_ON_DEVICE(L);
+    unsigned long long *d = nullptr;
+    LBM_CUDA(cudaMalloc(&d, sizeof(unsigned long long)));
+    cudaError_t e = cudaMemsetAsync(d, 0, sizeof(unsigned long long), L->stream);
+    if (e == cudaSuccess) {
+        const long long n = L->cfg.lnx * L->cfg.lny;
+        if (L->cfg.dtype == LB_F64)
+            checksum_kernel<double><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<double>(L), d);
+        else
+            checksum_kernel<float><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<float>(L), d);
+        e = cudaGetLastError();
+    }
+    unsigned long long h = 0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(&h, d, sizeof(h), cudaMemcpyDeviceToHost, L->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(L->stream);
+    cudaFree(d);
+    LBM_CUDA(e);
+    L->launches++;
+    *out = (uint64_t)h;
     return 0;
 }
 

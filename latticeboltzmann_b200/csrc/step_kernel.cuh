@@ -474,6 +474,42 @@ __global__ void moments_kernel(const __grid_constant__ StepParams<T> p, T *__res
     }
 }
 
+// Order-independent 64-bit digest of the current state: sum over populations and real cells of
+// mix(bits(f) , GLOBAL index), modulo 2^64.  Because the index is global, the digests of the blocks of any
+// decomposition add up to the digest of the undecomposed lattice: equal digests <=> bit-identical fields
+// (up to 2^-64 collisions) without moving the field off the device.
+__device__ __forceinline__ unsigned long long mix64(unsigned long long z)
+{
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+template <typename T>
+__global__ void checksum_kernel(const __grid_constant__ StepParams<T> p, unsigned long long *out)
+{
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;
+    const T *src = p.buf[par];
+    const long long n = (long long)p.lnx * p.lny;
+    unsigned long long acc = 0ull;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t / p.lny), l = (int)(t % p.lny);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) {
+            const T v = src[i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L)];
+            unsigned long long bits;
+            if (sizeof(T) == 8)
+                bits = (unsigned long long)__double_as_longlong((double)v);
+            else
+                bits = (unsigned long long)(unsigned int)__float_as_int((float)v);
+            const unsigned long long idx = ((unsigned long long)i * (unsigned long long)p.gnx + (unsigned long long)(p.x0 + k)) * (unsigned long long)p.gny + (unsigned long long)(p.y0 + l);
+            acc += mix64(bits ^ mix64(idx + 0x9e3779b97f4a7c15ull));
+        }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(out, acc);
+}
+
 // simple_flows: in-place collision of the whole current buffer (Couette's step order is
 // moments -> collide -> stream -> reflect, PoiseuilleFlow.py:107-111).
 template <typename T>

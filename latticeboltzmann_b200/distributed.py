@@ -165,6 +165,12 @@ class DistributedLattice:
     def health(self):
         self.block.health()
 
+    def checksum(self):
+        """Digest of the GLOBAL state: the per-block digests added modulo 2^64 (same value on every rank)."""
+        parts = [None] * self.world
+        _dist().all_gather_object(parts, self.block.checksum(), group=self.group)
+        return sum(parts) % (1 << 64)
+
     def gather_f(self, dst=0):
         return gather_blocks(self.block.download(), self.decomp, dst, self.group)
 

@@ -101,6 +101,25 @@ class Block:
         check(self.lib.lb_download_f(self.h, np_ptr(out)))
         return out
 
+    def download_rows(self, k_lo, k_hi, out=None):
+        """Rows [k_lo, k_hi) of the current state as a (9, k_hi - k_lo, lny) array."""
+        if out is None:
+            out = np.empty((9, k_hi - k_lo, self.lny), self.dtype)
+        assert out.flags.c_contiguous and out.dtype == self.dtype and out.shape == (9, k_hi - k_lo, self.lny)
+        check(self.lib.lb_download_rows(self.h, int(k_lo), int(k_hi), np_ptr(out)))
+        return out
+
+    def upload_rows(self, k_lo, k_hi, rows):
+        rows = self._host(rows, (9, k_hi - k_lo, self.lny))
+        check(self.lib.lb_upload_rows(self.h, int(k_lo), int(k_hi), np_ptr(rows)))
+
+    def checksum(self):
+        """64-bit digest of the current state (sum over cells of mix(bits, GLOBAL index) mod 2^64): the digests
+        of the blocks of any decomposition add up to the digest of the undecomposed lattice."""
+        d = ctypes.c_uint64()
+        check(self.lib.lb_checksum(self.h, ctypes.byref(d)))
+        return int(d.value)
+
     def init_equilibrium(self, rho=None, ux=None, uy=None):
         arrs = [None if a is None else self._host(np.broadcast_to(a, (self.lnx, self.lny)), (self.lnx, self.lny))
                 for a in (rho, ux, uy)]
@@ -294,6 +313,9 @@ class Lattice:
     def health(self):
         for b in self.blocks:
             b.health()
+
+    def checksum(self):
+        return sum(b.checksum() for b in self.blocks) % (1 << 64)
 
     @property
     def kernel_launches(self):

@@ -240,16 +240,16 @@ void FN(orc_periodic_run)(T *f, int64_t nx, int64_t ny, T omega, int64_t nsteps,
  * Used only as the "CPU-fused" informational baseline and as an independent
  * cross-check of the pull formulation the CUDA kernel uses.
  * rows [k_lo, k_hi) of dst are produced from src (both (9, nx, ny)).         */
-void FN(orc_cavity_step_pull_rows)(const T *src, T *dst, int64_t nx, int64_t ny, T omega, T u0,
-                                   int walls_lr, int do_collide, int64_t k_lo, int64_t k_hi)
+static void FN(orc_cavity_step_pull_rows_cols)(const T *src, T *dst, int64_t nx, int64_t ny, T omega, T u0,
+                                               int walls_lr, int do_collide, int64_t k, int64_t l_lo, int64_t l_hi)
 {
     static const int OPP[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
     const int E = 1, N = 2, W = 3, NE = 5, NW = 6, SW = 7, SE = 8;
     int64_t n = nx * ny, X = nx - 1, Tt = ny - 1;
     const T six_w = (T)6 * (T)(1.0 / 36.0);
 #define SRC(i, k, l) src[(i) * n + (k) * ny + (l)]
-    for (int64_t k = k_lo; k < k_hi; ++k) {
-        for (int64_t l = 0; l < ny; ++l) {
+    {
+        for (int64_t l = l_lo; l < l_hi; ++l) {
             T R[9], p[9];
             for (int i = 0; i < 9; ++i) {
                 int cx = FN(CX)[i], cy = FN(CY)[i];
@@ -268,6 +268,44 @@ void FN(orc_cavity_step_pull_rows)(const T *src, T *dst, int64_t nx, int64_t ny,
         }
     }
 #undef SRC
+}
+
+void FN(orc_cavity_step_pull_rows)(const T *src, T *dst, int64_t nx, int64_t ny, T omega, T u0,
+                                   int walls_lr, int do_collide, int64_t k_lo, int64_t k_hi)
+{
+    for (int64_t k = k_lo; k < k_hi; ++k)
+        FN(orc_cavity_step_pull_rows_cols)(src, dst, nx, ny, omega, u0, walls_lr, do_collide, k, 0, ny);
+}
+
+/* orc_cavity_step_pull_rows with the index arithmetic hoisted out of the column loop: the same per-cell rule
+ * (the literal function above is the definition; tests/test_oracle_golden.py compares the two bitwise), but
+ * columns 1 .. ny-2 -- which never see the top/bottom wall, the lid or the y wrap -- read their nine sources
+ * through row pointers instead of two modulo operations per population.  This is what makes the oracle usable
+ * at BASELINE's 4096^2 (tests/test_gpu_parity.py) and on the benchmarked strips (bench.py cpu_baseline leg). */
+void FN(orc_cavity_step_pull_rows_hoisted)(const T *src, T *dst, int64_t nx, int64_t ny, T omega, T u0,
+                                           int walls_lr, int do_collide, int64_t k_lo, int64_t k_hi)
+{
+    static const int OPP[9] = {0, 3, 4, 1, 2, 7, 8, 5, 6};
+    int64_t n = nx * ny, X = nx - 1;
+    for (int64_t k = k_lo; k < k_hi; ++k) {
+        /* the two wall columns of this row: the literal rule */
+        FN(orc_cavity_step_pull_rows_cols)(src, dst, nx, ny, omega, u0, walls_lr, do_collide, k, 0, 1);
+        if (ny > 1) FN(orc_cavity_step_pull_rows_cols)(src, dst, nx, ny, omega, u0, walls_lr, do_collide, k, ny - 1, ny);
+        const T *row[9];
+        int bounce[9];
+        for (int i = 0; i < 9; ++i) {
+            int cx = FN(CX)[i], cy = FN(CY)[i];
+            bounce[i] = walls_lr && ((cx == 1 && k == 0) || (cx == -1 && k == X));
+            /* source row pointer, already shifted by -cy: element l of it is src[i, k - cx, l - cy] */
+            row[i] = bounce[i] ? src + OPP[i] * n + k * ny : src + i * n + ((k - cx + nx) % nx) * ny - cy;
+        }
+        for (int64_t l = 1; l < ny - 1; ++l) {
+            T p[9];
+            for (int i = 0; i < 9; ++i) p[i] = row[i][l];
+            if (do_collide) FN(collide1)(p, 1, omega);
+            for (int i = 0; i < 9; ++i) dst[i * n + k * ny + l] = p[i];
+        }
+    }
 }
 
 /* Fully periodic fused pull step. */

@@ -1,4 +1,5 @@
-"""CPU tests of the output format (N2) and the single-process mpi4py stand-in (N3)."""
+"""CPU tests of the output format (N2) and the mpi4py stand-in (N3): one process, and a two-process gloo world
+that runs the reference's own cavity_opt2.py."""
 import os
 
 import numpy as np
@@ -48,8 +49,8 @@ def test_mpi4py_standin_runs_the_reference_io_sequence(tmp_path):
     assert comm.Get_size() == 1 and comm.Get_rank() == 0
     assert comm.Shift(0, -1) == (MPI.PROC_NULL, MPI.PROC_NULL)                 # :226-229: walls all around
     assert comm.Get_coords(0) == [0, 0]
-    with pytest.raises(RuntimeError):
-        MPI.COMM_WORLD.Create_cart((2, 1), periods=(False, False))
+    with pytest.raises(ValueError):
+        MPI.COMM_WORLD.Create_cart((2, 1), periods=(False, False))       # 2 processes needed, the world has 1
     g_kl = np.random.default_rng(1).random((6, 5))
     recv = np.full(5, 7.0)
     comm.Sendrecv(g_kl[0].copy(), MPI.PROC_NULL, recvbuf=recv, source=MPI.PROC_NULL)   # :192-194: no-op
@@ -89,3 +90,59 @@ def test_dropin_save_mpiio(tmp_path):
     assert np.array_equal(np.load(tmp_path / "a.npy"), g)
     assert np.array_equal(np.load(tmp_path / "b.npy"), g[1:-1, 1:])
     assert open(tmp_path / "a.npy", "rb").read(8) == npyio.MAGIC
+
+
+REF_SCRIPT = "/root/reference/simulators/parallel_lid_drive_cavity/cavity_opt2.py"
+
+
+def run_reference_script(tmp_path, backend, ndx, ndy, nx, ny, nsteps, dump_freq):
+    import socket
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    world = ndx * ndy
+    procs = []
+    for r in range(world):
+        env = dict(os.environ, RANK=str(r), WORLD_SIZE=str(world), LOCAL_RANK=str(r), MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+        procs.append(subprocess.Popen([sys.executable, os.path.join(here, "ref_script_worker.py"), REF_SCRIPT, backend, str(nsteps), str(dump_freq),
+                                       str(ndx), str(ndy), str(nx), str(ny), "float64"], cwd=str(tmp_path), env=env,
+                                      stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True))
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        assert p.returncode == 0, out[-3000:]
+
+
+def expected_velocity_dumps(nx, ny, nsteps, dump_freq):
+    """Single-rank result with the checker: after step i (i % dump_freq == 0) the script dumps
+    u = (f^T . c)/rho (cavity_opt2.py:279-283)."""
+    from oracle import oracle as orc
+    f = orc.init_equilibrium(nx, ny)
+    out = {}
+    for i in range(nsteps):
+        orc.cavity_run(f, 1.7, 1)
+        if i % dump_freq == 0:
+            rho = np.sum(f, axis=0)
+            out[i] = np.dot(f.T, orc.C_IC).T / rho
+    return out
+
+
+@pytest.mark.skipif(not os.path.exists(REF_SCRIPT), reason="the reference tree is not present on this machine")
+@pytest.mark.parametrize("ndx,ndy", [(1, 1), (1, 2)])
+def test_reference_cavity_script_runs_unmodified_under_the_shim(tmp_path, ndx, ndy):
+    """cavity_opt2.py itself (Create_cart, Shift, four Sendrecv per step, save_mpiio with Sub / Allreduce /
+    Exscan / MPI.File) on 1 and on 2 gloo ranks split in y -- the split for which the reference's decomposed
+    run equals its single-rank run -- against the single-rank checker."""
+    nx, ny, nsteps, dump_freq = 23, 18, 12, 5
+    run_reference_script(tmp_path, "cpu-checker", ndx, ndy, nx, ny, nsteps, dump_freq)
+    want = expected_velocity_dumps(nx, ny, nsteps, dump_freq)
+    for i, u in want.items():
+        for c, name in enumerate(("ux", "uy")):
+            got = np.load(tmp_path / ("%s_%d.npy" % (name, i)))
+            assert got.shape == (nx, ny)
+            assert np.max(np.abs(got - u[c])) < 1e-15, (name, i)
+    last = max(want)
+    assert np.array_equal(np.load(tmp_path / ("ux_%d.npy" % (nsteps - 1))), np.load(tmp_path / ("ux_%d.npy" % last)))   # :285-286 re-dumps the last moments

@@ -185,3 +185,38 @@ def test_opt2_numpy_structure_bitexact(golden_dir, dt):
         assert np.array_equal(f, g["out_" + tag]), tag
     t = opt2_numpy.run_independent_blocks(2, 32, 32, 1.7, 1, 2)
     assert t > 0
+
+
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+@pytest.mark.parametrize("walls_lr", [True, False])
+def test_hoisted_pull_equals_literal_pull(dt, walls_lr):
+    """The index-hoisted pull loop (what the 4096^2 GPU test and bench.py's strip check run) is the literal
+    per-cell rule: bitwise on ragged / degenerate shapes, and the threaded runner equals the literal
+    roll-then-overwrite sequence over many steps."""
+    for nx, ny in ((37, 29), (5, 2), (2, 2), (64, 50), (3, 7)):
+        f = orc.perturbed_state(nx, ny, np.dtype(dt), seed=nx + ny)
+        a, b = np.empty_like(f), np.empty_like(f)
+        orc.cavity_step_pull(f, a, 1.3, walls_lr=walls_lr)
+        orc.cavity_step_pull_hoisted(f, b, 1.3, walls_lr=walls_lr)
+        assert np.array_equal(a, b), (nx, ny)
+    f = orc.perturbed_state(45, 33, np.dtype(dt), seed=4)
+    ref = f.copy()
+    orc.cavity_run(ref, 1.7, 25, walls_lr=walls_lr)
+    got = orc.cavity_run_threaded(f.copy(), 1.7, 25, walls_lr=walls_lr, threads=3)
+    assert np.array_equal(got, ref)
+
+
+def test_bench_selfcheck_hashes_are_the_oracles(golden_dir):
+    """tests/golden/bench_parity.json (what bench.py compares the GPUs' gathered fields with at every N) is
+    what the oracle computes for latticeboltzmann_b200/selfcheck.py's cases."""
+    import json
+    import make_bench_parity
+    from latticeboltzmann_b200 import selfcheck
+    want = json.load(open(os.path.join(golden_dir, "bench_parity.json")))["sha256"]
+    assert set(want) == set(selfcheck.CASES)
+    name = "periodic_f32_517x1031_w1.2_s20"
+    assert make_bench_parity.expected(name) == want[name]
+    rho, ux, uy = selfcheck.fields(64, 48, "float32", 5, 7, 20, 11)
+    full = selfcheck.fields(64, 48, "float32")
+    assert all(np.array_equal(a, b[5:25, 7:18]) for a, b in zip((rho, ux, uy), full))       # blocks are slices of the global fields
+    assert all(np.array_equal(a.astype(np.float64), b) for a, b in zip(full, selfcheck.fields(64, 48, "float64")))   # exactly representable
