@@ -180,39 +180,26 @@ def run_reference_arm(args):
 
 
 def e2e_host_step(lat, steps):
-    """The step through the host-buffer C-ABI path: pinned host f -> device, one fused step,
-    f -> pinned host, every step (what a caller of the reference's stateless API pays).
-    Rank barriers order upload / ghost refresh / step across ranks (host-side, inside the timed region)."""
+    """The step through the host-buffer C-ABI path: pinned host f -> device, one fused step, f -> pinned host,
+    every step (what a caller of the reference's stateless API pays).  One block: lb_step_host, slab-pipelined.
+    Decomposed: DistributedLattice.step_host = rim upload, rank barrier, rim pushed into the neighbours' ghosts
+    over NVLink, rank barrier, then every rank's slab pipeline -- the barriers are inside the timed region."""
     import torch
     import torch.distributed as dist
     from latticeboltzmann_b200._lib import check, c_vp
     blk, lib = lat.block, lat.block.lib
-    host = torch.empty((9, blk.lnx, blk.lny), dtype=torch.float64).pin_memory()
-    ptr = c_vp(host.data_ptr())
-    check(lib.lb_download_f(blk.h, ptr))                       # current state as the first input
+    host_t = torch.empty((9, blk.lnx, blk.lny), dtype=torch.float64).pin_memory()
+    host = host_t.numpy()
+    check(lib.lb_download_f(blk.h, c_vp(host_t.data_ptr())))           # current state as the first input
 
-    single = dist.get_world_size() == 1
-
-    def one():
-        if single:                                             # slab-pipelined: H2D, compute, D2H overlap
-            check(lib.lb_step_host(blk.h, ptr, ptr, 128))
-            return
-        check(lib.lb_upload_f(blk.h, ptr))                     # H2D (synchronous on return)
-        dist.barrier()
-        check(lib.lb_halo_refresh(blk.h))
-        check(lib.lb_sync(blk.h))
-        dist.barrier()
-        check(lib.lb_step(blk.h, 1))
-        check(lib.lb_download_f(blk.h, ptr))                   # D2H (synchronous on return)
-
-    one()                                                      # warm-up
+    lat.step_host(host, host, 128)                                      # warm-up (creates streams / events / staging)
     dist.barrier()
     t0 = time.perf_counter()
     for _ in range(steps):
-        one()
+        lat.step_host(host, host, 128)
     dist.barrier()
     dt = time.perf_counter() - t0
-    return dt / steps, host.numel() * 8
+    return dt / steps, host_t.numel() * 8
 
 
 def parity_selfcheck(D, ndx, ndy, device):
@@ -392,7 +379,8 @@ def main():
             sec = D.max_over_ranks(sec)
             e2e = {"value": cells / sec / 1e6, "unit": "MLUPS", "h2d_bytes_per_step": nbytes, "d2h_bytes_per_step": nbytes,
                    "steps": args.e2e_steps, "path": ("lb_step_host: pinned host f[9,nx,ny] in/out every step, 128 slabs, H2D/compute/D2H overlapped" if world == 1 else
-                            "lb_upload_f + lb_halo_refresh + lb_step(1) + lb_download_f on pinned host f[9,lnx,lny] per rank; bytes are per rank")}
+                            "per rank: lb_step_host_begin (rim up) | barrier | lb_halo_refresh over NVLink | barrier | lb_step_host (128 slabs, H2D/compute/D2H "
+                            "overlapped) on pinned host f[9,lnx,lny]; bytes are per rank")}
         except Exception as exc:      # reported, never hidden
             e2e = {"value": None, "unit": "MLUPS", "error": repr(exc)}
     lat.close()

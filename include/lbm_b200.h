@@ -169,6 +169,15 @@ LB_API int lb_stream_only(lb_lattice *lat, int64_t nsteps);
  * host_in; both are C-contiguous (9, lnx, lny).  Single self-connected block; returns when
  * host_out is complete.  Pinned host memory is required for real overlap.              */
 LB_API int lb_step_host(lb_lattice *lat, const void *host_in, void *host_out, int nslabs);
+/* The same on a DECOMPOSED lattice (one block per rank / GPU), three phases per step with the ranks' own
+ * barrier between them -- the host-side schedule that replaces communicate() (cavity_opt2.py:179-210) when the
+ * state lives in host memory:
+ *   1. lb_step_host_begin(lat, host_in)   the block's rim (rows 0 / lnx-1, columns 0 / lny-1) goes to the device
+ *      [barrier]
+ *   2. lb_halo_refresh(lat); lb_sync(lat) every rank pushes its rim into its neighbours' ghosts over NVLink
+ *      [barrier]
+ *   3. lb_step_host(lat, host_in, host_out, nslabs)   slab-pipelined H2D / compute / D2H as above.        */
+LB_API int lb_step_host_begin(lb_lattice *lat, const void *host_in);
 /* Same, bracketed by CUDA events on the launching stream; returns elapsed ms.  */
 LB_API int lb_step_timed(lb_lattice *lat, int64_t nsteps, float *elapsed_ms);
 LB_API int64_t lb_steps_done(lb_lattice *lat);

@@ -67,6 +67,7 @@ SYMBOLS = {
     "lb_step": (ctypes.c_int, [c_vp, c_i64]),
     "lb_stream_only": (ctypes.c_int, [c_vp, c_i64]),
     "lb_step_host": (ctypes.c_int, [c_vp, c_vp, c_vp, ctypes.c_int]),
+    "lb_step_host_begin": (ctypes.c_int, [c_vp, c_vp]),
     "lb_step_timed": (ctypes.c_int, [c_vp, c_i64, _P(ctypes.c_float)]),
     "lb_steps_done": (c_i64, [c_vp]),
     "lb_health": (ctypes.c_int, [c_vp]),

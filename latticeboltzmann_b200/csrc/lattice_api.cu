@@ -58,6 +58,9 @@ struct lb_lattice {
     cudaStream_t s_h2d = nullptr, s_d2h = nullptr;
     std::vector<cudaEvent_t> ev_up, ev_done;
     cudaEvent_t ev_tail = nullptr, ev_fin = nullptr;
+    // decomposed host step: rim columns staged through pinned memory, begin/run handshake
+    void *h_cols = nullptr, *d_cols = nullptr;
+    bool host_begun = false;
 };
 
 namespace {
@@ -405,6 +408,8 @@ int lb_destroy(lb_lattice *L)
     for (auto e : L->ev_done) cudaEventDestroy(e);
     if (L->ev_tail) cudaEventDestroy(L->ev_tail);
     if (L->ev_fin) cudaEventDestroy(L->ev_fin);
+    if (L->h_cols) cudaFreeHost(L->h_cols);
+    if (L->d_cols) cudaFree(L->d_cols);
     if (L->s_h2d) cudaStreamDestroy(L->s_h2d);
     if (L->s_d2h) cudaStreamDestroy(L->s_d2h);
     if (L->ev0) cudaEventDestroy(L->ev0);
@@ -776,18 +781,74 @@ int copy_rows(lb_lattice *L, void *host, int par, int64_t k_lo, int64_t k_hi, bo
     return 0;
 }
 
-template <typename T>
-int step_host_pipelined(lb_lattice *L, const void *host_in, void *host_out, int nslabs)
+int host_step_resources(lb_lattice *L)
 {
-    const int64_t lnx = L->cfg.lnx;
-    if (nslabs < 1) nslabs = 1;
-    if (nslabs > lnx) nslabs = (int)lnx;
     if (!L->s_h2d) {
         LBM_CUDA(cudaStreamCreateWithFlags(&L->s_h2d, cudaStreamNonBlocking));
         LBM_CUDA(cudaStreamCreateWithFlags(&L->s_d2h, cudaStreamNonBlocking));
         LBM_CUDA(cudaEventCreateWithFlags(&L->ev_tail, cudaEventDisableTiming));
         LBM_CUDA(cudaEventCreateWithFlags(&L->ev_fin, cudaEventDisableTiming));
     }
+    return 0;
+}
+
+// columns l = 0 and l = lny-1 of all nine populations, packed as cols[(i*2 + side)*lnx + k], into buffer `par`
+template <typename T>
+__global__ void scatter_cols_kernel(const __grid_constant__ StepParams<T> p, const T *__restrict__ cols, int par)
+{
+    T *buf = p.buf[par];
+    const long long n = 18ll * p.lnx;
+    for (long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x; t < n; t += (long long)gridDim.x * blockDim.x) {
+        const int k = (int)(t % p.lnx), side = (int)((t / p.lnx) & 1), i = (int)(t / (2ll * p.lnx));
+        buf[(long long)i * p.pop_stride + (long long)(k + 1) * p.pitch + PAD_L + (side ? p.lny - 1 : 0)] = cols[t];
+    }
+}
+
+// Phase 1 of a DECOMPOSED host step: the block's rim (rows 0 and lnx-1, columns 0 and lny-1) of the host input goes
+// to the device first, so that lb_halo_refresh can push it into the neighbours' ghosts before any slab is computed.
+template <typename T>
+int step_host_begin(lb_lattice *L, const void *host_in)
+{
+    if (int r = host_step_resources(L)) return r;
+    const int64_t lnx = L->cfg.lnx, lny = L->cfg.lny;
+    const size_t col_bytes = (size_t)18 * lnx * sizeof(T);
+    if (!L->h_cols) {
+        LBM_CUDA(cudaMallocHost(&L->h_cols, col_bytes));
+        LBM_CUDA(cudaMalloc(&L->d_cols, col_bytes));
+    }
+    void *hin = const_cast<void *>(host_in);
+    const int par = L->cur;
+    LBM_CUDA(cudaEventRecord(L->ev_fin, L->stream));
+    LBM_CUDA(cudaStreamWaitEvent(L->s_h2d, L->ev_fin, 0));
+    if (int r = copy_rows(L, hin, par, 0, 1, true, L->s_h2d)) return r;
+    if (lnx > 1)
+        if (int r = copy_rows(L, hin, par, lnx - 1, lnx, true, L->s_h2d)) return r;
+    const T *h = static_cast<const T *>(host_in);
+    T *pack = static_cast<T *>(L->h_cols);
+    for (int i = 0; i < 9; ++i)
+        for (int side = 0; side < 2; ++side) {
+            const T *col = h + (size_t)i * lnx * lny + (side ? lny - 1 : 0);
+            T *dst = pack + ((size_t)i * 2 + side) * lnx;
+            for (int64_t k = 0; k < lnx; ++k) dst[k] = col[(size_t)k * lny];
+        }
+    LBM_CUDA(cudaMemcpyAsync(L->d_cols, L->h_cols, col_bytes, cudaMemcpyHostToDevice, L->s_h2d));
+    scatter_cols_kernel<T><<<grid_for(18 * lnx, 256), 256, 0, L->s_h2d>>>(make_params<T>(L), static_cast<const T *>(L->d_cols), par);
+    LBM_CUDA(cudaGetLastError());
+    LBM_CUDA(cudaStreamSynchronize(L->s_h2d));
+    L->launches++;
+    L->host_begun = true;
+    return 0;
+}
+
+// self_ring: the block closes its rings on itself and refreshes its own ghosts slab by slab; otherwise the ghosts
+// of the current buffer were filled beforehand (step_host_begin + lb_halo_refresh on every rank + barriers).
+template <typename T>
+int step_host_pipelined(lb_lattice *L, const void *host_in, void *host_out, int nslabs, bool self_ring)
+{
+    const int64_t lnx = L->cfg.lnx;
+    if (nslabs < 1) nslabs = 1;
+    if (nslabs > lnx) nslabs = (int)lnx;
+    if (int r = host_step_resources(L)) return r;
     while ((int)L->ev_up.size() < nslabs) {
         cudaEvent_t a, b;
         LBM_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -804,7 +865,8 @@ int step_host_pipelined(lb_lattice *L, const void *host_in, void *host_out, int 
     LBM_CUDA(cudaStreamWaitEvent(L->s_h2d, L->ev_fin, 0));
     LBM_CUDA(cudaStreamWaitEvent(L->s_d2h, L->ev_fin, 0));
     // the last row first: slab 0 pulls its periodic image (ghost row -1)
-    if (int r = copy_rows(L, hin, par, lnx - 1, lnx, true, L->s_h2d)) return r;
+    if (self_ring)
+        if (int r = copy_rows(L, hin, par, lnx - 1, lnx, true, L->s_h2d)) return r;
     LBM_CUDA(cudaEventRecord(L->ev_tail, L->s_h2d));
     for (int j = 0; j < nslabs; ++j) {
         if (int r = copy_rows(L, hin, par, lo(j), lo(j + 1), true, L->s_h2d)) return r;
@@ -812,13 +874,13 @@ int step_host_pipelined(lb_lattice *L, const void *host_in, void *host_out, int 
     }
     const long long n_rim = 2 * (L->cfg.lnx + L->cfg.lny);
     LBM_CUDA(cudaStreamWaitEvent(L->stream, L->ev_tail, 0));
-    halo_refresh_kernel<T><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(p, (int)lnx - 1, (int)lnx);
+    if (self_ring) halo_refresh_kernel<T><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(p, (int)lnx - 1, (int)lnx);
     LBM_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[0], 0));
-    halo_refresh_kernel<T><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(p, (int)lo(0), (int)lo(1));
+    if (self_ring) halo_refresh_kernel<T><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(p, (int)lo(0), (int)lo(1));
     for (int j = 0; j < nslabs; ++j) {
         if (j + 1 < nslabs) {   // slab j pulls from the first row of slab j+1 (and its ghost columns)
             LBM_CUDA(cudaStreamWaitEvent(L->stream, L->ev_up[j + 1], 0));
-            halo_refresh_kernel<T><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(p, (int)lo(j + 1), (int)lo(j + 2));
+            if (self_ring) halo_refresh_kernel<T><<<grid_for(n_rim, 256), 256, 0, L->stream>>>(p, (int)lo(j + 1), (int)lo(j + 2));
         }
         if (int r = launch_rows<T>(L, p, (int)lo(j), (int)lo(j + 1))) return r;
         LBM_CUDA(cudaEventRecord(L->ev_done[j], L->stream));
@@ -849,11 +911,25 @@ int lb_step_host(lb_lattice *L, const void *host_in, void *host_out, int nslabs)
 {
     if (int r = check_ready(L)) return r;
     if (!host_in || !host_out) return lbm_fail(LB_ERR_INVALID, "null host buffer");
+    bool self_ring = true;
     for (int d = 0; d < LB_NUM_DIRS; ++d)
-        if (L->nbr[d].base != L->base) return lbm_fail(LB_ERR_STATE, "lb_step_host needs a single self-connected block");
+        if (L->nbr[d].base != L->base) self_ring = false;
+    if (!self_ring && !L->host_begun)
+        return lbm_fail(LB_ERR_STATE, "a decomposed host step needs lb_step_host_begin + lb_halo_refresh (and rank barriers) before lb_step_host");
+    L->host_begun = false;
     LBM_ON_DEVICE(L);
-    return L->cfg.dtype == LB_F64 ? step_host_pipelined<double>(L, host_in, host_out, nslabs)
-                                  : step_host_pipelined<float>(L, host_in, host_out, nslabs);
+    return L->cfg.dtype == LB_F64 ? step_host_pipelined<double>(L, host_in, host_out, nslabs, self_ring)
+                                  : step_host_pipelined<float>(L, host_in, host_out, nslabs, self_ring);
+}
+
+/* First phase of a host step on a DECOMPOSED lattice (see lbm_b200.h). */
+int lb_step_host_begin(lb_lattice *L, const void *host_in)
+{
+    if (int r = check_ready(L)) return r;
+    if (!host_in) return lbm_fail(LB_ERR_INVALID, "null host buffer");
+    if (L->cfg.boundary > LB_CAVITY_XPERIODIC) return lbm_fail(LB_ERR_INVALID, "lb_step_host supports the periodic and cavity boundaries");
+    LBM_ON_DEVICE(L);
+    return L->cfg.dtype == LB_F64 ? step_host_begin<double>(L, host_in) : step_host_begin<float>(L, host_in);
 }
 
 int lb_step_timed(lb_lattice *L, int64_t nsteps, float *ms)

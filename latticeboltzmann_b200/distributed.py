@@ -151,6 +151,22 @@ class DistributedLattice:
     def step(self, n=1):
         self.block.step(n)
 
+    def step_host(self, f_in, f_out=None, nslabs=64):
+        """One step with this rank's block in HOST memory (pinned (9, lnx, lny) arrays; in place by default): the
+        host-side schedule that replaces communicate() (cavity_opt2.py:179-210) for a state that lives on the
+        host -- rim up, barrier, rim pushed into the neighbours' ghosts over NVLink, barrier, then the block's
+        slab pipeline (H2D / compute / D2H overlapped on three streams)."""
+        dist = _dist()
+        f_out = f_in if f_out is None else f_out
+        if self.world == 1:
+            return self.block.step_host(f_in, f_out, nslabs)
+        self.block.step_host_begin(f_in)
+        dist.barrier(self.group)
+        self.block.halo_refresh()
+        self.block.sync()
+        dist.barrier(self.group)
+        self.block.step_host(f_in, f_out, nslabs)
+
     def step_timed(self, n):
         """Barrier + sync, n steps timed with CUDA events on each rank's stream, max over ranks (ms)."""
         dist = _dist()
@@ -170,6 +186,21 @@ class DistributedLattice:
         parts = [None] * self.world
         _dist().all_gather_object(parts, self.block.checksum(), group=self.group)
         return sum(parts) % (1 << 64)
+
+    def save_checkpoint(self, fn, **meta):
+        """Populations of the whole lattice into ONE (9, nx, ny) .npy file (every rank writes its rows) + JSON sidecar."""
+        from . import npyio
+        dist = _dist()
+        npyio.save_checkpoint(fn, self.block.download(), self.decomp, self.rank, lambda: dist.barrier(self.group),
+                              dict(meta, steps_done=int(self.block.steps_done)))
+
+    def load_checkpoint(self, fn):
+        """Continue from a checkpoint written by any decomposition of the same lattice; returns its metadata."""
+        from . import npyio
+        f, meta = npyio.load_checkpoint_block(fn, self.decomp, self.rank)
+        self.block.upload(f.astype(self.block.dtype, copy=False))
+        self._refresh()
+        return meta
 
     def gather_f(self, dst=0):
         return gather_blocks(self.block.download(), self.decomp, dst, self.group)

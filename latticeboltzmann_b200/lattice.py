@@ -150,6 +150,14 @@ class Block:
                 raise TypeError("step_host needs C-contiguous %s arrays of shape (9, %d, %d)" % (self.dtype, self.lnx, self.lny))
         check(self.lib.lb_step_host(self.h, np_ptr(f_in), np_ptr(f_out), int(nslabs)))
 
+    def step_host_begin(self, f_in):
+        """Phase 1 of a host step on a decomposed lattice: this block's rim of `f_in` goes to the device (then:
+        barrier, halo_refresh + sync, barrier, step_host)."""
+        if not (isinstance(f_in, np.ndarray) and f_in.flags.c_contiguous and f_in.dtype == self.dtype
+                and f_in.shape == (9, self.lnx, self.lny)):
+            raise TypeError("step_host_begin needs a C-contiguous %s array of shape (9, %d, %d)" % (self.dtype, self.lnx, self.lny))
+        check(self.lib.lb_step_host_begin(self.h, np_ptr(f_in)))
+
     def sync(self):
         check(self.lib.lb_sync(self.h))
 
@@ -270,6 +278,20 @@ class Lattice:
             self.decomp.gather_into(g, r, b.download())
         return g
 
+    def save_checkpoint(self, fn, **meta):
+        from . import npyio
+        for r, b in enumerate(self.blocks):
+            npyio.save_checkpoint(fn, b.download(), self.decomp, r, None, dict(meta, steps_done=int(b.steps_done)))
+
+    def load_checkpoint(self, fn):
+        from . import npyio
+        meta = {}
+        for r, b in enumerate(self.blocks):
+            f, meta = npyio.load_checkpoint_block(fn, self.decomp, r)
+            b.upload(f.astype(self.dtype, copy=False))
+        self._refresh()
+        return meta
+
     def init_equilibrium(self, rho=None, ux=None, uy=None):
         """f = feq(rho, ux, uy) (c/d2q9.h:59-81); defaults rho=1, u=0 (cavity_opt2.py:265-269)."""
         for r, b in enumerate(self.blocks):
@@ -299,6 +321,23 @@ class Lattice:
         for _ in range(n):
             for b in self.blocks:
                 b.stream_only(1)
+
+    def step_host(self, f, nslabs=8):
+        """One step with the state in HOST memory (global (9, nx, ny) array, updated in place): per block the rim
+        goes up first, every block pushes it into its neighbours' ghosts, then each block runs its slab pipeline
+        (H2D / compute / D2H overlapped)."""
+        if len(self.blocks) == 1:
+            self.blocks[0].step_host(f, f, nslabs)
+            return f
+        parts = [np.ascontiguousarray(self.decomp.scatter(f, r)) for r in range(len(self.blocks))]
+        for b, p in zip(self.blocks, parts):
+            b.step_host_begin(p)
+        self._refresh()
+        for b, p in zip(self.blocks, parts):
+            b.step_host(p, p, nslabs)
+        for r, p in enumerate(parts):
+            self.decomp.gather_into(f, r, p)
+        return f
 
     def step_timed(self, n):
         """Milliseconds for n steps (CUDA events on the launching stream; single block only)."""

@@ -20,7 +20,12 @@ from .. import npyio
 
 
 def run(ndx, ndy, nx, ny, dtype=np.float64, nsteps=100000, dump_freq=10000, omega=1.7, u0=0.1, arith="exact",
-        outdir=".", verbose=True):
+        outdir=".", verbose=True, checkpoint_freq=0, restart=None):
+    """Steps are numbered like the reference's loop variable (`for i in range(nsteps)`, :272).  After step i with
+    i % dump_freq == 0 the velocities are dumped (:279-283); after the loop they are dumped once more as
+    ux/uy_{nsteps-1}.npy (:285-286 -- from the FINAL state here; the reference re-writes the moments of its last
+    periodic dump).  Additions the reference lacks: every `checkpoint_freq` completed steps the populations go to
+    f_{steps}.npy (+ .json), and `restart=<that file>` continues a run bit-identically."""
     rank, world, local = D.init_process_group()
     if rank == 0 and verbose:
         print("Running in parallel on {} processes (one per GPU).".format(world))
@@ -29,24 +34,39 @@ def run(ndx, ndy, nx, ny, dtype=np.float64, nsteps=100000, dump_freq=10000, omeg
         print("Using {} floating point data type.".format(np.dtype(dtype)))
     lat = D.DistributedLattice(nx, ny, ndx, ndy, "cavity", omega=float(omega), u_wall=u0, dtype=dtype,
                                arith=arith, device=local)
-    lat.init_equilibrium()                                        # :265-269
     import torch.distributed as dist
-    i = 0
+    done = 0                                                      # completed steps = next value of the loop variable
+    if restart:
+        done = int(lat.load_checkpoint(restart).get("steps_completed", 0))
+    else:
+        lat.init_equilibrium()                                    # :265-269
     written = []
-    while i < nsteps:
-        lat.step(1)                                               # step i
-        if i % dump_freq == 0:                                    # :279 (dumps after step 0, dump_freq, ...)
-            _, ux, uy = lat.block.moments()                       # :280-281
-            for name, field in (("ux", ux), ("uy", uy)):
-                fn = os.path.join(outdir, "{}_{}.npy".format(name, i))
-                npyio.save_field(fn, field, lat.decomp, rank, dist.barrier)
-                written.append(fn)
-        nxt = min(nsteps, (i // dump_freq + 1) * dump_freq)       # run to the next dump step in one go
-        if nxt - (i + 1) > 0:
-            lat.step(nxt - (i + 1))
-        i = nxt
+
+    def dump(i):
+        _, ux, uy = lat.block.moments()                           # :280-281
+        for name, field in (("ux", ux), ("uy", uy)):
+            fn = os.path.join(outdir, "{}_{}.npy".format(name, i))
+            npyio.save_field(fn, field, lat.decomp, rank, dist.barrier)
+            written.append(fn)
+
+    while done < nsteps:
+        # run to the next step index that is dumped (i % dump_freq == 0) or checkpointed, in one go
+        stops = [nsteps, (done + dump_freq - 1) // dump_freq * dump_freq + 1]
+        if checkpoint_freq:
+            stops.append((done // checkpoint_freq + 1) * checkpoint_freq)
+        nxt = min(s for s in stops if s > done)
+        lat.step(nxt - done)
+        done = nxt
+        if (done - 1) % dump_freq == 0:                           # :279, i = done - 1
+            dump(done - 1)
+        if checkpoint_freq and done % checkpoint_freq == 0 and done < nsteps:
+            fn = os.path.join(outdir, "f_{}.npy".format(done))
+            lat.save_checkpoint(fn, steps_completed=done, omega=float(omega), u0=u0, nx=nx, ny=ny)
+            written.append(fn)
         if rank == 0 and verbose:
-            sys.stdout.write("=== Step {}/{} ===\r".format(i, nsteps))
+            sys.stdout.write("=== Step {}/{} ===\r".format(done, nsteps))
+    if nsteps > 0 and (nsteps - 1) % dump_freq != 0:
+        dump(nsteps - 1)                                          # :285-286
     lat.health()
     lat.close()
     return written
