@@ -214,6 +214,11 @@ LB_API int lb_double_step_phase(lb_lattice *lat, int phase);
 LB_API int lb_temporal_active(lb_lattice *lat);
 /* lb_step replays a CUDA graph of 64 fused steps for long runs (default on).                */
 LB_API int lb_set_use_graph(lb_lattice *lat, int on);
+/* L2-resident lattices (a single self-connected block of at most 2^20 cells that does not use temporal
+ * blocking): lb_step(n >= 2) advances all n steps in ONE cooperative launch with a grid-wide barrier per step
+ * -- shear probe, Couette's collide-first order and Poiseuille's pressure columns run inside it -- instead of
+ * one (simple_flows: three) launches per step.  Bit-identical; default on; LBM_RESIDENT=0|1 overrides.       */
+LB_API int lb_set_resident(lb_lattice *lat, int on);
 /* Geometry queries (elements). */
 LB_API int64_t lb_pitch(lb_lattice *lat);
 LB_API int64_t lb_pop_stride(lb_lattice *lat);

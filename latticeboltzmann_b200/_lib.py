@@ -76,6 +76,7 @@ SYMBOLS = {
     "lb_probe_shear_read": (ctypes.c_int, [c_vp, c_vp, c_i64]),
     "lb_set_rows_per_tile": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "lb_set_halo_timeout_ms": (ctypes.c_int, [c_vp, c_i64]),
+    "lb_set_resident": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "lb_set_use_graph": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "lb_set_temporal": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "lb_double_step_phase": (ctypes.c_int, [c_vp, ctypes.c_int]),

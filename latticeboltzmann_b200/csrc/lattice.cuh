@@ -50,6 +50,7 @@ struct DevState {
     unsigned int error;                    // != 0: a halo flag wait timed out
     unsigned int frame_done;               // temporal blocking: frame-kernel CTAs finished in the running launch
     unsigned long long fflag_in[NUM_DIRS]; // temporal blocking: level-(n+1) frame ghosts pushed by the neighbour in slot d
+    unsigned long long grid_bar;           // resident multi-step kernel: arrivals at its grid barrier (monotone)
 };
 
 // ---- temporal blocking (two time steps per pass over HBM), temporal.cuh ----------------------------

@@ -15,6 +15,7 @@
 #include "api_common.h"
 #include "step_kernel.cuh"
 #include "temporal.cuh"
+#include "resident.cuh"
 
 using namespace lbm;
 
@@ -49,8 +50,11 @@ struct lb_lattice {
     int64_t steps = 0;
     int cur = 0;                 // host mirror of DevState::cur (buffer holding the current state)
     int64_t launches = 0;
+    bool use_resident = true;    // L2-resident single blocks: one cooperative launch for many steps (resident.cuh)
+    unsigned long long grid_bar = 0;   // host mirror of DevState::grid_bar
+    int resident_ctas = 0;       // co-resident CTAs of the resident kernel on this device (0: not queried yet)
     // shear probe
-    void *d_uyk = nullptr, *d_series = nullptr;
+    void *d_uyk = nullptr, *d_series = nullptr, *d_prod = nullptr;
     int64_t probe_capacity = 0, probe_l_local = -1, probe_step0 = 0;
     // scratch for moments
     void *d_mom = nullptr;
@@ -297,6 +301,84 @@ int launch_sf_prologue(lb_lattice *L)
     return 0;
 }
 
+// ---- resident multi-step kernel (resident.cuh): L2-resident single blocks ---------------------------------
+constexpr long long RESIDENT_MAX_CELLS = 1ll << 20;     // 2 x 72 B x 2^20 cells = 151 MB would not stay in L2; above this the per-step kernels win anyway
+
+bool resident_ok(const lb_lattice *L)
+{
+    if (!L->use_resident || temporal_ok(L)) return false;
+    if (L->cfg.lnx * L->cfg.lny > RESIDENT_MAX_CELLS) return false;
+    for (int d = 0; d < LB_NUM_DIRS; ++d)
+        if (!L->nbr[d].connected || L->nbr[d].base != L->base) return false;   // the wrap is index arithmetic: one self-connected block
+    return true;
+}
+
+template <typename T, int BC, bool EXACT>
+int launch_resident_bc(lb_lattice *L, int64_t nsteps)
+{
+    auto kernel = resident_kernel<T, BC, EXACT>;
+    if (!L->resident_ctas) {
+        int per_sm = 0, sms = 0;
+        LBM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, RES_THREADS, 0));
+        LBM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->cfg.device));
+        L->resident_ctas = per_sm * sms;
+        if (L->resident_ctas < 2) return lbm_fail(LB_ERR_CUDA, "the resident kernel does not fit the device");
+    }
+    StepParams<T> p = make_params<T>(L);
+    const bool probe = L->d_series != nullptr;
+    const long long n = (long long)p.lnx * p.lny;
+    long long workers = (n + RES_THREADS - 1) / RES_THREADS;
+    if (workers > L->resident_ctas - (probe ? 1 : 0)) workers = L->resident_ctas - (probe ? 1 : 0);
+    const int grid = (int)workers + (probe ? 1 : 0);
+    while (nsteps > 0) {
+        const int64_t chunk = nsteps > (1 << 20) ? (1 << 20) : nsteps;
+        ResidentArgs a{};
+        a.nsteps = chunk;
+        a.bar_base = L->grid_bar;
+        a.couette_shift = BC == BC_SF_COUETTE ? 1 : 0;
+        a.probe_l = probe ? (int)L->probe_l_local : -1;
+        a.uy_k = L->d_uyk;
+        a.series = L->d_series;
+        a.capacity = L->probe_capacity;
+        a.step0 = (unsigned long long)L->probe_step0;
+        a.prod = L->d_prod;
+        void *args[] = {&p, &a};
+        LBM_CUDA(cudaLaunchCooperativeKernel((void *)kernel, dim3(grid), dim3(RES_THREADS), args, 0, L->stream));
+        L->grid_bar += (unsigned long long)grid * (unsigned long long)(chunk + (BC == BC_SF_POISEUILLE ? 1 : 0) + (a.couette_shift ? 1 : 0));
+        L->launches++;
+        L->steps += chunk;
+        L->cur ^= (int)(chunk & 1);
+        nsteps -= chunk;
+    }
+    // the kernel works without the ghost frame: re-establish it for whatever runs next (fused steps, moments, ...)
+    halo_refresh_kernel<T><<<grid_for(2ll * (p.lnx + p.lny), 256), 256, 0, L->stream>>>(p, 0, p.lnx);
+    L->launches++;
+    LBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
+template <typename T>
+int launch_resident(lb_lattice *L, int64_t nsteps)
+{
+    const bool exact = L->cfg.arith == LB_ARITH_EXACT;
+    switch (L->cfg.boundary) {
+    case LB_PERIODIC:
+        return exact ? launch_resident_bc<T, BC_PERIODIC, true>(L, nsteps) : launch_resident_bc<T, BC_PERIODIC, false>(L, nsteps);
+    case LB_CAVITY:
+        return exact ? launch_resident_bc<T, BC_CAVITY, true>(L, nsteps) : launch_resident_bc<T, BC_CAVITY, false>(L, nsteps);
+    case LB_CAVITY_XPERIODIC:
+        return exact ? launch_resident_bc<T, BC_CAVITY_XPERIODIC, true>(L, nsteps) : launch_resident_bc<T, BC_CAVITY_XPERIODIC, false>(L, nsteps);
+    case LB_SF_COUETTE:
+        return launch_resident_bc<T, BC_SF_COUETTE, true>(L, nsteps);
+    case LB_SF_POISEUILLE:
+        return launch_resident_bc<T, BC_SF_POISEUILLE, true>(L, nsteps);
+    case LB_SF_SLIDING_LID:
+        return launch_resident_bc<T, BC_SF_SLIDING_LID, true>(L, nsteps);
+    default:
+        return lbm_fail(LB_ERR_INVALID, "unknown boundary mode %d", L->cfg.boundary);
+    }
+}
+
 int check_ready(lb_lattice *L)
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
@@ -386,6 +468,7 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     }
     L->rows_per_tile = cfg->dtype == LB_F64 ? 4 : 8;     // measured optima
     if (const char *t = getenv("LBM_TEMPORAL")) L->temporal = (atoi(t) >= 0 && atoi(t) <= 2) ? atoi(t) : 0;
+    if (const char *t = getenv("LBM_RESIDENT")) L->use_resident = atoi(t) != 0;
     if (const char *t = getenv("LBM_T2_ROWS")) if (atoi(t) > 0) L->t2_rows = atoi(t);
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
@@ -403,6 +486,7 @@ int lb_destroy(lb_lattice *L)
     for (auto &kv : L->ipc_open) cudaIpcCloseMemHandle(kv.second);
     if (L->d_uyk) cudaFree(L->d_uyk);
     if (L->d_series) cudaFree(L->d_series);
+    if (L->d_prod) cudaFree(L->d_prod);
     if (L->d_mom) cudaFree(L->d_mom);
     for (auto e : L->ev_up) cudaEventDestroy(e);
     for (auto e : L->ev_done) cudaEventDestroy(e);
@@ -479,6 +563,13 @@ int lb_set_use_graph(lb_lattice *L, int on)
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
     L->use_graph = on != 0;
+    return 0;
+}
+
+int lb_set_resident(lb_lattice *L, int on)
+{
+    if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
+    L->use_resident = on != 0;
     return 0;
 }
 
@@ -688,6 +779,12 @@ int lb_step(lb_lattice *L, int64_t nsteps)
             nsteps -= 2;
         }
         LBM_CUDA(cudaGetLastError());
+    }
+    // L2-resident single blocks: ONE cooperative launch for all remaining steps (probe and simple_flows step orders inside).
+    if (nsteps >= 2 && resident_ok(L)) {
+        int r = L->cfg.dtype == LB_F64 ? launch_resident<double>(L, nsteps) : (sf ? lbm_fail(LB_ERR_INVALID, "simple_flows is fp64") : launch_resident<float>(L, nsteps));
+        if (r) return r;
+        nsteps = 0;
     }
     // Long runs of plain fused steps replay a CUDA graph (one host call per GRAPH_STEPS launches).
     if (L->use_graph && !sf && !L->d_series && nsteps >= 2 * GRAPH_STEPS) {
@@ -990,6 +1087,9 @@ int lb_probe_shear_enable(lb_lattice *L, int64_t l_global, const void *uy_k, int
     LBM_ON_DEVICE(L);
     if (L->d_uyk) cudaFree(L->d_uyk);
     if (L->d_series) cudaFree(L->d_series);
+    if (L->d_prod) cudaFree(L->d_prod);
+    L->d_uyk = L->d_series = L->d_prod = nullptr;
+    LBM_CUDA(cudaMalloc(&L->d_prod, (size_t)2 * L->cfg.lnx * L->elem));
     LBM_CUDA(cudaMalloc(&L->d_uyk, (size_t)L->cfg.lnx * L->elem));
     LBM_CUDA(cudaMalloc(&L->d_series, (size_t)capacity * L->elem));
     LBM_CUDA(cudaMemcpy(L->d_uyk, uy_k, (size_t)L->cfg.lnx * L->elem, cudaMemcpyHostToDevice));

@@ -1,0 +1,202 @@
+// Resident multi-step kernel for L2-resident lattices (BASELINE configs[0] and [1]: the 300 x 200 shear wave, the
+// 512 x 512 simple_flows cases).
+//
+// A lattice of a few hundred thousand cells fits the 126 MB L2 twice over, so its time step is not HBM-bound but
+// launch- and latency-bound: one fused launch per step costs ~5 us, three launches per step (simple_flows) ~25 us.
+// Here ONE cooperative launch advances the block `nsteps` steps: every CTA keeps its cells, a grid-wide barrier
+// (one atomic arrival + one acquire poll per CTA) separates the steps, and everything that used to be a separate
+// launch runs inside the loop:
+//   * the periodic wrap is index arithmetic on the single self-connected block (no ghost frame, no halo push, no
+//     flags) -- the ghosts are refreshed once, by the caller, after the launch;
+//   * the shear-wave amplitude probe (shear_wave_opt2.py:99) is an in-kernel epilogue: the cells of the probe
+//     column leave uy * uy_k in a double-buffered array and one extra CTA reduces it (same fixed tree as
+//     shear_probe_kernel) while the workers already compute the next step;
+//   * Couette's collide-before-stream order (PoiseuilleFlow.py:107-111) is a phase shift: with s' = SR(C(s)) the
+//     kernel keeps c = C(s) between its passes (c' = C(SR(c))), i.e. one in-place collision first, fused passes,
+//     and a last pass without collision -- the stored state between lb_step calls is always the reference's s;
+//   * Poiseuille's pressure columns (PoiseuilleFlow.py:76-88: rows 0 and X rewritten from rows X-1 and 1 at the
+//     START of a step) are produced at the END of the previous pass by the threads that have just computed the
+//     cells of rows X-1 and 1 (they hold the nine post-collision populations in registers); the plain values of
+//     rows 0 and X, which nothing would ever read, are not computed in between.  Only the first pass of a launch
+//     rewrites the columns in a phase of its own, and the last pass leaves the plain rows, so the stored state
+//     between lb_step calls is the reference's.
+// Arithmetic, boundary rules and their order are the functions of step_kernel.cuh / temporal.cuh, so results are
+// bit-identical to single fused steps.
+#pragma once
+#include "temporal.cuh"
+
+namespace lbm {
+
+// Threads per CTA of the resident kernel.  Every CTA costs one serialised atomic arrival per barrier, so fewer,
+// fatter CTAs shorten the barrier; measured (300 x 200 / 512^2 simple_flows) in profiles/r02_small_lattices.log.
+#ifndef LBM_RES_THREADS
+#define LBM_RES_THREADS 512
+#endif
+constexpr int RES_THREADS = LBM_RES_THREADS;
+
+struct ResidentArgs {
+    long long nsteps;
+    unsigned long long bar_base;    // DevState::grid_bar when the launch starts
+    int couette_shift;              // 1: collide in place first, last pass without collision
+    int probe_l;                    // local column of the shear probe, -1: none
+    const void *uy_k;               // lnx values
+    void *series;                   // capacity values
+    long long capacity;
+    unsigned long long step0;       // step count when the probe was enabled
+    void *prod;                     // 2 * lnx values: uy(k, probe_l) * uy_k[k] of the last two steps
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All CTAs of the (cooperative, hence co-resident) grid: arrive, then wait until `target` arrivals were counted.
+__device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long target)
+{
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        atomicAdd(bar, 1ull);
+        while (ld_acquire_gpu(bar) < target) {}
+    }
+    __syncthreads();
+}
+
+// level n: the current buffer of a single self-connected block, periodic wrap by index arithmetic
+template <typename T>
+struct SrcWrap {
+    const StepParams<T> &p;
+    const T *src;
+    int k, l;
+    template <int I>
+    __device__ __forceinline__ T pull() const
+    {
+        int kk = k - cx_of(I), ll = l - cy_of(I);
+        if (cx_of(I) == 1 && kk < 0) kk = p.lnx - 1;
+        if (cx_of(I) == -1 && kk >= p.lnx) kk = 0;
+        if (cy_of(I) == 1 && ll < 0) ll = p.lny - 1;
+        if (cy_of(I) == -1 && ll >= p.lny) ll = 0;
+        return __ldcg(src + (long long)I * p.pop_stride + (long long)(kk + 1) * p.pitch + (ll + PAD_L));
+    }
+    __device__ __forceinline__ T own(int i) const { return __ldcg(src + (long long)i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L)); }
+};
+
+template <typename T, int BC, bool EXACT>
+__global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_constant__ StepParams<T> p, const ResidentArgs a)
+{
+    __shared__ T red[RES_THREADS];
+    DevState *st = p.st;
+    const unsigned long long step = *(volatile unsigned long long *)&st->step;
+    int par = (int)*(volatile unsigned int *)&st->cur;
+    const bool probe = a.probe_l >= 0;
+    const int workers = (int)gridDim.x - (probe ? 1 : 0);
+    const bool reducer = probe && (int)blockIdx.x == workers;          // the extra CTA: probe reductions only
+    const long long n = (long long)p.lnx * p.lny;
+    const long long stride = (long long)workers * RES_THREADS;
+    const long long t0 = (long long)blockIdx.x * RES_THREADS + threadIdx.x;
+    unsigned long long bar = a.bar_base;
+    const T *uy_k = static_cast<const T *>(a.uy_k);
+    T *prod = static_cast<T *>(a.prod);
+    T *series = static_cast<T *>(a.series);
+
+    if (a.couette_shift) {              // c = C(s): in place on the current buffer
+        if (!reducer)
+            for (long long t = t0; t < n; t += stride) {
+                const int k = (int)(t / p.lny), l = (int)(t - (long long)k * p.lny);
+                T *q = p.buf[par] + (long long)(k + 1) * p.pitch + (l + PAD_L);
+                T f[9];
+#pragma unroll
+                for (int i = 0; i < 9; ++i) f[i] = __ldcg(q + i * p.pop_stride);
+                sf_collide<T>(f, p.omega);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) q[i * p.pop_stride] = f[i];
+            }
+        bar += gridDim.x;
+        grid_barrier(&st->grid_bar, bar);
+    }
+
+    for (long long s = 0; s < a.nsteps; ++s) {
+        const T *__restrict__ src = p.buf[par];
+        T *__restrict__ dst = p.buf[par ^ 1];
+        const bool last = s == a.nsteps - 1;
+        if (BC == BC_SF_POISEUILLE && s == 0) {   // pressure columns of the stored state: a phase of its own, once per launch
+            if (!reducer)
+                for (long long t = t0; t < p.lny; t += stride) sf_pressure_cell<T>(p, p.buf[par], (int)t);
+            bar += gridDim.x;
+            grid_barrier(&st->grid_bar, bar);
+        }
+        const bool collide = !(a.couette_shift && last);
+        if (!reducer) {
+            for (long long t = t0; t < n; t += stride) {
+                const int k = (int)(t / p.lny), l = (int)(t - (long long)k * p.lny);
+                if (BC == BC_SF_POISEUILLE && !last && (k == 0 || k == p.lnx - 1)) continue;   // replaced by the pressure columns below
+                const SrcWrap<T> sw{p, src, k, l};
+                T f[9];
+                pull9<T>(sw, f);
+                const long long c = (long long)(k + 1) * p.pitch + (l + PAD_L);
+                if (BC >= BC_SF_COUETTE)
+                    sf_wall_rules<T, BC>(p, src, c, k, l, f);
+                else
+                    wall_rules<T, BC>(p, sw, f, k, l);
+                if (collide) {
+                    if (BC >= BC_SF_COUETTE)
+                        sf_collide<T>(f, p.omega);
+                    else
+                        d2q9_collide<T, EXACT>(f, p.omega);
+                }
+                T *dp = dst + c;
+#pragma unroll
+                for (int i = 0; i < 9; ++i) dp[i * p.pop_stride] = f[i];
+                if (BC == BC_SF_POISEUILLE && !last && (k == 1 || k == p.lnx - 2)) {
+                    // PoiseuilleFlow.py:78-88 for the NEXT step, from this cell's new populations (== sf_pressure_cell)
+                    T e[9], en[9], rho, ux, uy;
+                    sf_moments<T>(f, rho, ux, uy);
+                    sf_equilibrium<T>(rho, ux, uy, e);
+#pragma unroll 1
+                    for (int side = 0; side < 2; ++side) {
+                        if (k != (side == 0 ? p.lnx - 2 : 1)) continue;
+                        sf_equilibrium<T>(side == 0 ? p.rho_in : p.rho_out, ux, uy, en);
+                        T *d = dst + (long long)((side == 0 ? 0 : p.lnx - 1) + 1) * p.pitch + (l + PAD_L);
+#pragma unroll
+                        for (int i = 0; i < 9; ++i) d[i * p.pop_stride] = rn_add(en[i], rn_sub(f[i], e[i]));
+                    }
+                }
+                if (probe && l == a.probe_l) {
+                    T r, x, y;
+                    d2q9_moments<T>(f, r, x, y);
+                    prod[(s & 1) * p.lnx + k] = y * uy_k[k];
+                }
+            }
+        }
+        bar += gridDim.x;
+        grid_barrier(&st->grid_bar, bar);
+        if (reducer) {                  // shear_wave_opt2.py:99 for the step just completed (same tree as shear_probe_kernel)
+            T acc = T(0);
+            for (int k = threadIdx.x; k < p.lnx; k += RES_THREADS) acc += __ldcg(prod + (s & 1) * p.lnx + k);
+            red[threadIdx.x] = acc;
+            __syncthreads();
+            for (int w = RES_THREADS / 2; w > 0; w >>= 1) {
+                if ((int)threadIdx.x < w) red[threadIdx.x] += red[threadIdx.x + w];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) {
+                const long long idx = (long long)(step + (unsigned long long)s + 1ull - a.step0) - 1;
+                if (idx >= 0 && idx < a.capacity) series[idx] = red[0] * T(2) / T(p.gnx);
+            }
+            __syncthreads();
+        }
+        par ^= 1;
+    }
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) {      // after the last barrier: every cell of the final state is stored
+        const unsigned long long done = step + (unsigned long long)a.nsteps;
+        *(volatile unsigned int *)&st->cur = (unsigned int)par;
+        *(volatile unsigned long long *)&st->step = done;
+        for (int d = 0; d < NUM_DIRS; ++d) st->flag_in[d] = done;   // the caller refreshes the ghosts next (stream order)
+    }
+}
+
+}  // namespace lbm

@@ -125,30 +125,14 @@ __device__ __forceinline__ void push_halo(const StepParams<T> &p, int par, int k
 #undef LBM_PUSH
 }
 
-// One cell: gather, boundary rules, collide, store (+ halo push on rim tiles).
-template <typename T, int BC, bool EXACT, bool COLLIDE, bool RIM>
-__device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__restrict__ src, T *__restrict__ dst,
-                                            int par_dst, int k, int l)
+// simple_flows flavour: explicit wall LAYERS at l = 0 / T (and k = 0 / X for the sliding
+// lid); after the periodic pull, populations that entered a wall layer are copied back into the adjacent fluid
+// row/column -- written here as a gather from the pre-stream state `src` (c = the cell's own element offset).
+// Single block only, so local == global coordinates.
+template <typename T, int BC>
+__device__ __forceinline__ void sf_wall_rules(const StepParams<T> &p, const T *__restrict__ src, long long c, int k, int l, T (&f)[9])
 {
     const long long S = p.pop_stride, P = p.pitch;
-    const long long c = (long long)(k + 1) * P + (l + PAD_L);
-    const char *sp = reinterpret_cast<const char *>(src + c);
-    T f[9];
-#pragma unroll
-    for (int i = 0; i < 9; ++i) {
-        if (RIM && cy_of(i) == 1 && l == 0)                  // source (k-cx, -1): ghost column below
-            f[i] = __ldcg(p.ycol[par_dst ^ 1] + (0 * 3 + ycol_slot(i)) * (long long)(p.lnx + 2) + (k - cx_of(i) + 1));
-        else if (RIM && cy_of(i) == -1 && l == p.lny - 1)    // source (k-cx, lny): ghost column above
-            f[i] = __ldcg(p.ycol[par_dst ^ 1] + (1 * 3 + ycol_slot(i)) * (long long)(p.lnx + 2) + (k - cx_of(i) + 1));
-        else
-            f[i] = ld_f<RIM>(reinterpret_cast<const T *>(sp + p.ld_off[i]));
-    }
-
-    if (RIM && BC >= BC_SF_COUETTE) {
-        // simple_flows flavour: explicit wall LAYERS at l = 0 / T (and k = 0 / X for
-        // the sliding lid); after the periodic pull, populations that entered a wall layer are copied back
-        // into the adjacent fluid row/column -- written here as a gather from the pre-stream state.
-        // Single block only, so local == global coordinates.
         const int X = p.lnx - 1, Tt = p.lny - 1;
 #define LBM_PRE(I, DK, DL) ld_f<true>(src + (long long)(I) * S + c + (long long)(DK) * P + (DL))
         if (BC == BC_SF_SLIDING_LID && l >= 1 && l <= Tt - 1) {     // slidingLid.py:72-78
@@ -171,6 +155,29 @@ __device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__r
             }
         }
 #undef LBM_PRE
+}
+
+// One cell: gather, boundary rules, collide, store (+ halo push on rim tiles).
+template <typename T, int BC, bool EXACT, bool COLLIDE, bool RIM>
+__device__ __forceinline__ void update_cell(const StepParams<T> &p, const T *__restrict__ src, T *__restrict__ dst,
+                                            int par_dst, int k, int l)
+{
+    const long long S = p.pop_stride, P = p.pitch;
+    const long long c = (long long)(k + 1) * P + (l + PAD_L);
+    const char *sp = reinterpret_cast<const char *>(src + c);
+    T f[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        if (RIM && cy_of(i) == 1 && l == 0)                  // source (k-cx, -1): ghost column below
+            f[i] = __ldcg(p.ycol[par_dst ^ 1] + (0 * 3 + ycol_slot(i)) * (long long)(p.lnx + 2) + (k - cx_of(i) + 1));
+        else if (RIM && cy_of(i) == -1 && l == p.lny - 1)    // source (k-cx, lny): ghost column above
+            f[i] = __ldcg(p.ycol[par_dst ^ 1] + (1 * 3 + ycol_slot(i)) * (long long)(p.lnx + 2) + (k - cx_of(i) + 1));
+        else
+            f[i] = ld_f<RIM>(reinterpret_cast<const T *>(sp + p.ld_off[i]));
+    }
+
+    if (RIM && BC >= BC_SF_COUETTE) {
+        sf_wall_rules<T, BC>(p, src, c, k, l, f);
     } else if (RIM && BC != BC_PERIODIC) {
         // SURVEY.md App. A.2 == cavity_opt2.py:133-177 as a gather.  Predicates on
         // global coordinates; the wall sits half a cell outside the lattice.
@@ -534,27 +541,30 @@ __global__ void sf_collide_inplace_kernel(const __grid_constant__ StepParams<T> 
 // k = X of the current buffer:  f[:,0,l] = feq(rho_in, u[X-1,l]) + (f[:,X-1,l] - feq[:,X-1,l]),
 //                               f[:,X,l] = feq(rho_out, u[1,l]) + (f[:,1,l]   - feq[:,1,l]).
 template <typename T>
+__device__ __forceinline__ void sf_pressure_cell(const StepParams<T> &p, T *buf, int l)
+{
+    const int X = p.lnx - 1;
+#pragma unroll
+    for (int side = 0; side < 2; ++side) {
+        const int ks = side == 0 ? X - 1 : 1, kd = side == 0 ? 0 : X;
+        const T *q = buf + (long long)(ks + 1) * p.pitch + (l + PAD_L);
+        T f[9], e[9], en[9], rho, ux, uy;
+#pragma unroll
+        for (int i = 0; i < 9; ++i) f[i] = __ldcg(q + i * p.pop_stride);
+        sf_moments<T>(f, rho, ux, uy);
+        sf_equilibrium<T>(rho, ux, uy, e);
+        sf_equilibrium<T>(side == 0 ? p.rho_in : p.rho_out, ux, uy, en);
+        T *d = buf + (long long)(kd + 1) * p.pitch + (l + PAD_L);
+#pragma unroll
+        for (int i = 0; i < 9; ++i) d[i * p.pop_stride] = rn_add(en[i], rn_sub(f[i], e[i]));
+    }
+}
+template <typename T>
 __global__ void sf_pressure_kernel(const __grid_constant__ StepParams<T> p)
 {
     const int par = (int)*(volatile unsigned int *)&p.st->cur;
     T *buf = p.buf[par];
-    const int X = p.lnx - 1;
-    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < p.lny; l += gridDim.x * blockDim.x) {
-#pragma unroll
-        for (int side = 0; side < 2; ++side) {
-            const int ks = side == 0 ? X - 1 : 1, kd = side == 0 ? 0 : X;
-            const T *q = buf + (long long)(ks + 1) * p.pitch + (l + PAD_L);
-            T f[9], e[9], en[9], rho, ux, uy;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) f[i] = q[i * p.pop_stride];
-            sf_moments<T>(f, rho, ux, uy);
-            sf_equilibrium<T>(rho, ux, uy, e);
-            sf_equilibrium<T>(side == 0 ? p.rho_in : p.rho_out, ux, uy, en);
-            T *d = buf + (long long)(kd + 1) * p.pitch + (l + PAD_L);
-#pragma unroll
-            for (int i = 0; i < 9; ++i) d[i * p.pop_stride] = rn_add(en[i], rn_sub(f[i], e[i]));
-        }
-    }
+    for (int l = blockIdx.x * blockDim.x + threadIdx.x; l < p.lny; l += gridDim.x * blockDim.x) sf_pressure_cell<T>(p, buf, l);
 }
 
 // shear_wave_opt2.py:99 -- one block; deterministic tree reduction.

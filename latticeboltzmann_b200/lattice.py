@@ -80,6 +80,10 @@ class Block:
     def temporal_active(self):
         return bool(self.lib.lb_temporal_active(self.h))
 
+    def set_resident(self, on):
+        """Allow / forbid the resident multi-step kernel (L2-resident single blocks, one launch for many steps)."""
+        check(self.lib.lb_set_resident(self.h, int(bool(on))))
+
     def set_use_graph(self, on):
         check(self.lib.lb_set_use_graph(self.h, int(bool(on))))
 

@@ -14,6 +14,14 @@ def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
 
 
+@pytest.fixture(params=["resident", "per-step"])
+def stepping_path(request, monkeypatch):
+    """Small single-block lattices can advance through the resident multi-step kernel (one cooperative launch,
+    default) or through one fused launch per step; tests that use this fixture run once on each path."""
+    monkeypatch.setenv("LBM_RESIDENT", "1" if request.param == "resident" else "0")
+    return request.param
+
+
 @pytest.fixture(scope="session")
 def golden_dir():
     return GOLDEN

@@ -46,6 +46,7 @@ def test_periodic_stream_golden_bitexact(golden_dir):
         lat.close()
 
 
+@pytest.mark.usefixtures("stepping_path")
 @pytest.mark.parametrize("dt", ["float64", "float32"])
 @pytest.mark.parametrize("boundary", ["periodic", "cavity", "cavity_xperiodic"])
 def test_fused_step_bitexact_vs_oracle(dt, boundary):
@@ -73,6 +74,7 @@ def test_fused_step_bitexact_vs_oracle(dt, boundary):
         assert np.array_equal(got, ref), (nx, ny, float(np.abs(got - ref).max()))
 
 
+@pytest.mark.usefixtures("stepping_path")
 def test_cavity_1000_steps_exact_and_fast():
     """BASELINE gate: f, rho within 1e-12 relative, u within 1e-12 of max|u| after 1000 fp64 steps.
     EXACT mode is bit-identical; FAST mode (FMA contraction, reciprocal) is the documented deviation."""
@@ -165,6 +167,7 @@ def test_decomposition_bit_exact(boundary, ndx, ndy):
     assert np.array_equal(ref, chk)
 
 
+@pytest.mark.usefixtures("stepping_path")
 def test_shear_wave_viscosity_300x200():
     """BASELINE config 1: 300x200 periodic, omega=1, 1000 steps; on-device amplitude probe."""
     lb = require_gpu()
@@ -247,9 +250,10 @@ def test_halo_timeout_is_reported_not_hung():
     lat.close()
 
 
-def test_graph_replay_equals_single_launches():
+def test_graph_replay_equals_single_launches(monkeypatch):
     """lb_step replays a CUDA graph of 64 fused steps for long runs; same bits as step-by-step launches."""
     lb = require_gpu()
+    monkeypatch.setenv("LBM_RESIDENT", "0")      # the per-step launch path is the subject here
     f0 = orc.perturbed_state(70, 530, seed=5)
     outs = []
     for use_graph, temporal in ((True, 1), (False, 1), (True, 2), (False, 2)):

@@ -14,6 +14,9 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "latticeboltzmann_b200", "csrc", "variants")
 
 VARIANTS = {
+    "res256": ["LBM_RES_THREADS=256"],
+    "res512": ["LBM_RES_THREADS=512"],
+    "res1024": ["LBM_RES_THREADS=1024"],
     "tma1": ["LBM_T2_TMA=1", "LBM_T2_STAGES=1", "LBM_T2_MINB=4"],
     "tma2": ["LBM_T2_TMA=1", "LBM_T2_STAGES=2", "LBM_T2_MINB=3"],
     "tma4": ["LBM_T2_TMA=1", "LBM_T2_STAGES=4", "LBM_T2_MINB=2"],
