@@ -57,7 +57,9 @@ typedef enum lb_boundary {
     LB_CAVITY_XPERIODIC = 2,  /* same with `if True:` -> `if False:` (cavity_opt2.py:147)   */
     LB_SF_COUETTE = 3,        /* simple_flows/PoiseuilleFlow.py:93-111 (wall layers)        */
     LB_SF_POISEUILLE = 4,     /* simple_flows/PoiseuilleFlow.py:129-148                     */
-    LB_SF_SLIDING_LID = 5     /* simple_flows/slidingLid.py:68-108                          */
+    LB_SF_SLIDING_LID = 5,    /* simple_flows/slidingLid.py:68-108                          */
+    LB_SF_TABLE = 6           /* simple_flows family with a per-cell boundary TABLE (lb_set_boundary_table):
+                                 slidingLidMPI.py:180-204, experimantal_flows/obstacle_canal.py:413-458 */
 } lb_boundary;
 
 /* Arithmetic of the collision.
@@ -219,6 +221,15 @@ LB_API int lb_set_use_graph(lb_lattice *lat, int on);
  * -- shear probe, Couette's collide-first order and Poiseuille's pressure columns run inside it -- instead of
  * one (simple_flows: three) launches per step.  Bit-identical; default on; LBM_RESIDENT=0|1 overrides.       */
 LB_API int lb_set_resident(lb_lattice *lat, int on);
+/* LB_SF_TABLE: the walls of the simple_flows family as a per-cell gather table.  The reference writes them as a
+ * sequence of overlapping slice assignments on the streamed array (slidingLidMPI.py:180-204, obstacle_canal.py:
+ * 413-458); replayed symbolically on the host (latticeboltzmann_b200/boundary_table.py) that sequence becomes, for
+ * each of the `n` listed cells (flat index k*lny + l), the pre-stream source of every population (flat element
+ * index i*lnx*lny + k*lny + l into the (9, lnx, lny) state, src[9*j + i]) and an additive constant (add[9*j + i]):
+ *     post[i, cell_j] = pre[src[9 j + i]] + add[9 j + i]
+ * All other cells stream periodically; then moments and collision (simple_flows arithmetic, fp64, one block).
+ * The table is copied to the device; calling it again replaces the table.                                        */
+LB_API int lb_set_boundary_table(lb_lattice *lat, int64_t n, const int64_t *cells, const int64_t *src, const double *add);
 /* Geometry queries (elements). */
 LB_API int64_t lb_pitch(lb_lattice *lat);
 LB_API int64_t lb_pop_stride(lb_lattice *lat);

@@ -16,7 +16,7 @@ c_vp = ctypes.c_void_p
 
 LB_F32, LB_F64 = 0, 1
 BOUNDARY = {"periodic": 0, "cavity": 1, "cavity_xperiodic": 2,
-            "sf_couette": 3, "sf_poiseuille": 4, "sf_sliding_lid": 5}
+            "sf_couette": 3, "sf_poiseuille": 4, "sf_sliding_lid": 5, "sf_table": 6}
 ARITH = {"exact": 0, "fast": 1}
 NUM_DIRS = 8
 # (dx, dy) of direction slot d -- include/lbm_b200.h
@@ -76,6 +76,7 @@ SYMBOLS = {
     "lb_probe_shear_read": (ctypes.c_int, [c_vp, c_vp, c_i64]),
     "lb_set_rows_per_tile": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "lb_set_halo_timeout_ms": (ctypes.c_int, [c_vp, c_i64]),
+    "lb_set_boundary_table": (ctypes.c_int, [c_vp, c_i64, c_vp, c_vp, c_vp]),
     "lb_set_resident": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "lb_set_use_graph": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "lb_set_temporal": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),

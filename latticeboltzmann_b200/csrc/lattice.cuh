@@ -121,6 +121,13 @@ struct StepParams {
     // them straight from the constant bank (no registers): ld_off[i] addresses the pull source
     // (i, k - cx_i, l - cy_i).
     long long ld_off[9];
+    // per-cell boundary table (BC_SF_TABLE): tab_n cells (flat k*lny + l), for each the element offsets of its nine
+    // pre-stream sources inside a buffer and nine additive constants; one bit per lattice cell marks the listed ones
+    const int *tab_cells;
+    const long long *tab_src;
+    const T *tab_add;
+    const unsigned int *tab_mask;
+    int tab_n;
     NbrView<T> nbr[NUM_DIRS];
 };
 

@@ -64,6 +64,12 @@ struct lb_lattice {
     cudaEvent_t ev_tail = nullptr, ev_fin = nullptr;
     // decomposed host step: rim columns staged through pinned memory, begin/run handshake
     void *h_cols = nullptr, *d_cols = nullptr;
+    // per-cell boundary table (LB_SF_TABLE)
+    int *d_tab_cells = nullptr;
+    long long *d_tab_src = nullptr;
+    void *d_tab_add = nullptr;
+    unsigned int *d_tab_mask = nullptr;
+    int tab_n = 0;
     bool host_begun = false;
 };
 
@@ -147,6 +153,11 @@ StepParams<T> make_params(lb_lattice *L)
     for (int i = 0; i < 9; ++i) {
         p.ld_off[i] = (long long)sizeof(T) * (i * L->pop_stride - cx_of(i) * L->pitch - cy_of(i));
     }
+    p.tab_cells = L->d_tab_cells;
+    p.tab_src = L->d_tab_src;
+    p.tab_add = static_cast<const T *>(L->d_tab_add);
+    p.tab_mask = L->d_tab_mask;
+    p.tab_n = L->tab_n;
     p.sys_scope = 0;
     p.halo_timeout_ns = L->halo_timeout_ns;
     for (int d = 0; d < LB_NUM_DIRS; ++d) {
@@ -198,6 +209,8 @@ int launch_step(lb_lattice *L, bool collide)
         return launch_step_bc<T, BC_SF_POISEUILLE, true>(L, p, collide);
     case LB_SF_SLIDING_LID:
         return launch_step_bc<T, BC_SF_SLIDING_LID, true>(L, p, collide);
+    case LB_SF_TABLE:
+        return launch_step_bc<T, BC_SF_TABLE, true>(L, p, collide);
     default:
         return lbm_fail(LB_ERR_INVALID, "unknown boundary mode %d", L->cfg.boundary);
     }
@@ -374,6 +387,8 @@ int launch_resident(lb_lattice *L, int64_t nsteps)
         return launch_resident_bc<T, BC_SF_POISEUILLE, true>(L, nsteps);
     case LB_SF_SLIDING_LID:
         return launch_resident_bc<T, BC_SF_SLIDING_LID, true>(L, nsteps);
+    case LB_SF_TABLE:
+        return launch_resident_bc<T, BC_SF_TABLE, true>(L, nsteps);
     default:
         return lbm_fail(LB_ERR_INVALID, "unknown boundary mode %d", L->cfg.boundary);
     }
@@ -414,7 +429,7 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
         cfg->x0 + cfg->lnx > cfg->gnx || cfg->y0 + cfg->lny > cfg->gny)
         return lbm_fail(LB_ERR_INVALID, "inconsistent block geometry");
     if (cfg->lnx > (1ll << 30) || cfg->lny > (1ll << 30)) return lbm_fail(LB_ERR_INVALID, "block extent too large");
-    if (cfg->boundary < LB_PERIODIC || cfg->boundary > LB_SF_SLIDING_LID) return lbm_fail(LB_ERR_INVALID, "unknown boundary");
+    if (cfg->boundary < LB_PERIODIC || cfg->boundary > LB_SF_TABLE) return lbm_fail(LB_ERR_INVALID, "unknown boundary");
     if (cfg->arith != LB_ARITH_EXACT && cfg->arith != LB_ARITH_FAST) return lbm_fail(LB_ERR_INVALID, "unknown arith");
     // A wall-bounded box needs two distinct wall rows/columns: with a single row the reference's
     // sequential overwrites (cavity_opt2.py:134-177) alias top and bottom and the gather form does not apply.
@@ -492,6 +507,10 @@ int lb_destroy(lb_lattice *L)
     for (auto e : L->ev_done) cudaEventDestroy(e);
     if (L->ev_tail) cudaEventDestroy(L->ev_tail);
     if (L->ev_fin) cudaEventDestroy(L->ev_fin);
+    if (L->d_tab_cells) cudaFree(L->d_tab_cells);
+    if (L->d_tab_src) cudaFree(L->d_tab_src);
+    if (L->d_tab_add) cudaFree(L->d_tab_add);
+    if (L->d_tab_mask) cudaFree(L->d_tab_mask);
     if (L->h_cols) cudaFreeHost(L->h_cols);
     if (L->d_cols) cudaFree(L->d_cols);
     if (L->s_h2d) cudaStreamDestroy(L->s_h2d);
@@ -563,6 +582,49 @@ int lb_set_use_graph(lb_lattice *L, int on)
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
     L->use_graph = on != 0;
+    return 0;
+}
+
+int lb_set_boundary_table(lb_lattice *L, int64_t n, const int64_t *cells, const int64_t *src, const double *add)
+{
+    if (!L || n < 0 || (n > 0 && (!cells || !src || !add))) return lbm_fail(LB_ERR_INVALID, "bad argument");
+    if (L->cfg.boundary != LB_SF_TABLE) return lbm_fail(LB_ERR_STATE, "the lattice was not created with LB_SF_TABLE");
+    const int64_t lnx = L->cfg.lnx, lny = L->cfg.lny, ncell = lnx * lny;
+    if (n > ncell) return lbm_fail(LB_ERR_INVALID, "more table cells than lattice cells");
+    std::vector<int> h_cells((size_t)n);
+    std::vector<long long> h_src((size_t)n * 9);
+    std::vector<unsigned int> h_mask((size_t)(ncell + 31) / 32, 0u);
+    for (int64_t j = 0; j < n; ++j) {
+        if (cells[j] < 0 || cells[j] >= ncell) return lbm_fail(LB_ERR_INVALID, "table cell %lld is outside the lattice", (long long)cells[j]);
+        if ((h_mask[cells[j] >> 5] >> (cells[j] & 31)) & 1u) return lbm_fail(LB_ERR_INVALID, "table cell %lld is listed twice", (long long)cells[j]);
+        h_mask[cells[j] >> 5] |= 1u << (cells[j] & 31);
+        h_cells[j] = (int)cells[j];
+        for (int i = 0; i < 9; ++i) {
+            const int64_t e = src[9 * j + i];
+            if (e < 0 || e >= 9 * ncell) return lbm_fail(LB_ERR_INVALID, "table source %lld is outside the state", (long long)e);
+            const int64_t ch = e / ncell, k = (e - ch * ncell) / lny, l = e - ch * ncell - k * lny;
+            h_src[9 * j + i] = ch * L->pop_stride + (k + 1) * L->pitch + l + PAD_L;      // element offset inside a buffer
+        }
+    }
+    LBM_ON_DEVICE(L);
+    LBM_CUDA(cudaStreamSynchronize(L->stream));
+    if (L->d_tab_cells) cudaFree(L->d_tab_cells);
+    if (L->d_tab_src) cudaFree(L->d_tab_src);
+    if (L->d_tab_add) cudaFree(L->d_tab_add);
+    if (L->d_tab_mask) cudaFree(L->d_tab_mask);
+    L->d_tab_cells = nullptr; L->d_tab_src = nullptr; L->d_tab_add = nullptr; L->d_tab_mask = nullptr;
+    L->tab_n = 0;
+    LBM_CUDA(cudaMalloc(&L->d_tab_mask, h_mask.size() * sizeof(unsigned int)));
+    LBM_CUDA(cudaMemcpy(L->d_tab_mask, h_mask.data(), h_mask.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    if (n > 0) {
+        LBM_CUDA(cudaMalloc(&L->d_tab_cells, (size_t)n * sizeof(int)));
+        LBM_CUDA(cudaMalloc(&L->d_tab_src, (size_t)n * 9 * sizeof(long long)));
+        LBM_CUDA(cudaMalloc(&L->d_tab_add, (size_t)n * 9 * sizeof(double)));
+        LBM_CUDA(cudaMemcpy(L->d_tab_cells, h_cells.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
+        LBM_CUDA(cudaMemcpy(L->d_tab_src, h_src.data(), (size_t)n * 9 * sizeof(long long), cudaMemcpyHostToDevice));
+        LBM_CUDA(cudaMemcpy(L->d_tab_add, add, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    L->tab_n = (int)n;
     return 0;
 }
 
@@ -805,6 +867,13 @@ int lb_step(lb_lattice *L, int64_t nsteps)
         L->launches++;
         L->steps++;
         L->cur ^= 1;
+        if (L->cfg.boundary == LB_SF_TABLE && L->tab_n > 0) {
+            // the listed cells again, from the previous buffer with their table; then the ghosts of the rim cells among them
+            const StepParams<double> p = make_params<double>(L);
+            table_cells_kernel<double><<<grid_for(L->tab_n, 128), 128, 0, L->stream>>>(p);
+            halo_refresh_kernel<double><<<grid_for(2ll * (p.lnx + p.lny), 256), 256, 0, L->stream>>>(p, 0, p.lnx);
+            L->launches += 2;
+        }
         if (L->d_series) {
             if (L->cfg.dtype == LB_F64)
                 shear_probe_kernel<double><<<1, 256, 0, L->stream>>>(make_params<double>(L), (int)L->probe_l_local, (const double *)L->d_uyk,

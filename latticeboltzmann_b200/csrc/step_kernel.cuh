@@ -29,7 +29,7 @@
 
 namespace lbm {
 
-enum BoundaryKind { BC_PERIODIC = 0, BC_CAVITY = 1, BC_CAVITY_XPERIODIC = 2, BC_SF_COUETTE = 3, BC_SF_POISEUILLE = 4, BC_SF_SLIDING_LID = 5 };
+enum BoundaryKind { BC_PERIODIC = 0, BC_CAVITY = 1, BC_CAVITY_XPERIODIC = 2, BC_SF_COUETTE = 3, BC_SF_POISEUILLE = 4, BC_SF_SLIDING_LID = 5, BC_SF_TABLE = 6 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
@@ -132,6 +132,7 @@ __device__ __forceinline__ void push_halo(const StepParams<T> &p, int par, int k
 template <typename T, int BC>
 __device__ __forceinline__ void sf_wall_rules(const StepParams<T> &p, const T *__restrict__ src, long long c, int k, int l, T (&f)[9])
 {
+    if (BC == BC_SF_TABLE) return;      // walls come from the per-cell table (table_cell), everything else streams periodically
     const long long S = p.pop_stride, P = p.pitch;
         const int X = p.lnx - 1, Tt = p.lny - 1;
 #define LBM_PRE(I, DK, DL) ld_f<true>(src + (long long)(I) * S + c + (long long)(DK) * P + (DL))
@@ -479,6 +480,37 @@ __global__ void moments_kernel(const __grid_constant__ StepParams<T> p, T *__res
         if (ux) ux[t] = x;
         if (uy) uy[t] = y;
     }
+}
+
+// BC_SF_TABLE: cell j of the boundary table -- gather the nine populations from their tabulated pre-stream sources
+// (+ constant), collide, store (lattice.cuh: tab_*; latticeboltzmann_b200/boundary_table.py builds the table).
+template <typename T>
+__device__ __forceinline__ void table_cell(const StepParams<T> &p, const T *__restrict__ src, T *__restrict__ dst, int j)
+{
+    const int cell = p.tab_cells[j];
+    const int k = cell / p.lny, l = cell - k * p.lny;
+    T f[9];
+#pragma unroll
+    for (int i = 0; i < 9; ++i) {
+        const T v = __ldcg(src + p.tab_src[9 * (long long)j + i]);
+        const T c = p.tab_add[9 * (long long)j + i];
+        f[i] = c == T(0) ? v : rn_add(v, c);      // x + 0 would turn -0 into +0; a plain copy must stay a copy
+    }
+    sf_collide<T>(f, p.omega);
+    T *dp = dst + (long long)(k + 1) * p.pitch + (l + PAD_L);
+#pragma unroll
+    for (int i = 0; i < 9; ++i) dp[i * p.pop_stride] = f[i];
+}
+__device__ __forceinline__ bool table_has(const unsigned int *mask, long long cell) { return (mask[cell >> 5] >> (cell & 31)) & 1u; }
+
+// Per-step path of BC_SF_TABLE: after step_kernel streamed + collided EVERY cell periodically into the new current
+// buffer, the listed cells are recomputed from the previous buffer (still intact: A/B) with their table.
+template <typename T>
+__global__ void table_cells_kernel(const __grid_constant__ StepParams<T> p)
+{
+    const int par = (int)*(volatile unsigned int *)&p.st->cur;      // already flipped by step_kernel
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < p.tab_n; j += gridDim.x * blockDim.x)
+        table_cell<T>(p, p.buf[par ^ 1], p.buf[par], j);
 }
 
 // Order-independent 64-bit digest of the current state: sum over populations and real cells of

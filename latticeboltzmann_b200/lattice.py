@@ -80,6 +80,16 @@ class Block:
     def temporal_active(self):
         return bool(self.lib.lb_temporal_active(self.h))
 
+    def set_boundary_table(self, cells, src, add):
+        """Per-cell boundary table of an "sf_table" lattice (boundary_table.py: cells (n,), src (n, 9), add (n, 9))."""
+        cells = np.ascontiguousarray(cells, dtype=np.int64)
+        src = np.ascontiguousarray(src, dtype=np.int64)
+        add = np.ascontiguousarray(add, dtype=np.float64)
+        n = cells.shape[0]
+        if src.shape != (n, 9) or add.shape != (n, 9):
+            raise ValueError("expected src and add of shape (%d, 9)" % n)
+        check(self.lib.lb_set_boundary_table(self.h, n, np_ptr(cells), np_ptr(src), np_ptr(add)))
+
     def set_resident(self, on):
         """Allow / forbid the resident multi-step kernel (L2-resident single blocks, one launch for many steps)."""
         check(self.lib.lb_set_resident(self.h, int(bool(on))))
@@ -375,6 +385,12 @@ class Lattice:
             self.decomp.gather_into(ux, r, lx)
             self.decomp.gather_into(uy, r, ly)
         return rho, ux, uy
+
+    def set_boundary_table(self, cells, src, add):
+        """Walls of the simple_flows family as a per-cell gather table (boundary "sf_table", one block)."""
+        if len(self.blocks) != 1:
+            raise ValueError("boundary tables run on a single block")
+        self.blocks[0].set_boundary_table(cells, src, add)
 
     def probe_shear_enable(self, uy_k, capacity, l_probe=None):
         """Record shear_wave_opt2.py:99's amplitude after every step, on the device."""

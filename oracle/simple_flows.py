@@ -140,3 +140,62 @@ def sliding_lid_step(f, omega, uw):
     f[...] = post
     rho, ux, uy = collide(f, omega)
     return ux
+
+
+def sliding_lid_mpi_step(f, omega, uw):
+    """slidingLidMPI.py:264-268 on one rank: stream, bounce_back_choosen (:180-204, all four walls, FULL index
+    ranges, applied in place in the reference's order so that later lines read what earlier lines wrote),
+    moments, collision.  Array (L+2, L+2)."""
+    g = pull(f)
+    g[3, -2, :] = g[1, -1, :]
+    g[6, -2, :] = g[8, -1, :]
+    g[7, -2, :] = g[5, -1, :]
+    g[1, 1, :] = g[3, 0, :]
+    g[5, 1, :] = g[7, 0, :]
+    g[8, 1, :] = g[6, 0, :]
+    g[2, :, 1] = g[4, :, 0]
+    g[5, :, 1] = g[7, :, 0]
+    g[6, :, 1] = g[8, :, 0]
+    g[4, :, -2] = g[2, :, -1]
+    g[7, :, -2] = g[5, :, -1] - 1 / 6 * uw
+    g[8, :, -2] = g[6, :, -1] + 1 / 6 * uw
+    f[...] = g
+    collide(f, omega)
+
+
+def obstacle_channel_step(f, omega, x0, x1, y0, y1, uw=0.0):
+    """experimantal_flows/obstacle_canal.py:270-275 without the pressure step: stream, bounce_back_choosen with
+    bottom / top walls (:320-329), apply_obstacle (:413-458, its ranges and channel pairs as written), moments,
+    collision.  x is periodic."""
+    g = pull(f)
+    g[2, :, 1] = g[4, :, 0]
+    g[5, :, 1] = g[7, :, 0]
+    g[6, :, 1] = g[8, :, 0]
+    g[4, :, -2] = g[2, :, -1]
+    g[7, :, -2] = g[5, :, -1] - 1 / 6 * uw
+    g[8, :, -2] = g[6, :, -1] + 1 / 6 * uw
+    ys, xs = slice(y0, y1), slice(x0, x1)
+    g[3, x0 - 1, ys] = g[1, x0, ys]
+    g[7, x0 - 1, ys] = g[5, x0, ys]
+    g[6, x0 - 1, ys] = g[8, x0, ys]
+    g[1, x1 + 1, ys] = g[3, x1, ys]
+    g[5, x1 + 1, ys] = g[7, x1, ys]
+    g[6, x1 + 1, ys] = g[8, x1, ys]
+    g[2, xs, y1 + 1] = g[4, xs, y1]
+    g[5, xs, y1 + 1] = g[7, xs, y1]
+    g[6, xs, y1 + 1] = g[8, xs, y1]
+    g[4, xs, y0 - 1] = g[2, xs, y0]
+    g[7, xs, y0 - 1] = g[5, xs, y0]
+    g[8, xs, y0 - 1] = g[6, xs, y0]
+    f[...] = g
+    collide(f, omega)
+
+
+def table_step(f, omega, cells, src, add):
+    """The gather form the CUDA kernel applies (latticeboltzmann_b200/boundary_table.py): periodic pull, the
+    listed cells from their tabulated pre-stream sources + constants, then collision."""
+    g = pull(f).reshape(9, -1)
+    vals = f.reshape(-1)[src]
+    g[:, cells] = np.where(add != 0, vals + add, vals).T
+    f[...] = g.reshape(f.shape)
+    collide(f, omega)

@@ -22,6 +22,8 @@ What each fixture pins (reference file:line):
   simple_couette.npz      PoiseuilleFlow.py:25-74,93-111                   (bit-exact vs numpy oracle)
   simple_poiseuille.npz   PoiseuilleFlow.py:76-88,129-148                  (bit-exact vs numpy oracle)
   simple_sliding_lid.npz  slidingLid.py:33-108                             (bit-exact vs numpy oracle)
+  table_sliding_lid_mpi.npz  slidingLidMPI.py:123-204,264-268 (full-range bounce, one rank)      (bit-exact)
+  table_obstacle_channel.npz obstacle_canal.py:303-339,413-458 (methods of obstacleWindTunnel)   (bit-exact)
 """
 import ast
 import os
@@ -231,6 +233,69 @@ def gen_simple_flows():
     np.savez_compressed(os.path.join(OUT, "simple_sliding_lid.npz"), **out)
 
 
+def lift_methods(path, cls, methods, preset=None):
+    """The named methods of a class of an unmodified reference file, as plain functions taking `self`."""
+    with open(os.path.join(REF, path)) as fh:
+        tree = ast.parse(fh.read())
+    ns = {"np": np}
+    ns.update(preset or {})
+    body = []
+    for node in tree.body:
+        if isinstance(node, ast.ClassDef) and node.name == cls:
+            body = [n for n in node.body if isinstance(n, ast.FunctionDef) and n.name in methods]
+    assert len(body) == len(methods), (path, cls, methods)
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    return ns
+
+
+def gen_table_flows():
+    from types import SimpleNamespace as NS
+    vs = np.array([[0, 1, 0, -1, 0, 1, -1, -1, 1], [0, 0, 1, 0, -1, 1, 1, -1, -1]]).T
+    # slidingLidMPI.py on one rank: stream -> bounce_back_choosen (all four walls, FULL ranges) -> moments -> collision (:264-268)
+    path = "simulators/simple_flows/slidingLidMPI.py"
+    ns = lift(path, funcs=("stream", "equilibrium", "collision", "caluculate_rho_ux_uy", "bounce_back_choosen"),
+              preset={"velocity_set": vs})
+    L, uw, omega, nsteps = 11, 0.1, 1.2, 40
+    n = L + 2
+    info = NS(boundaries_info=NS(apply_right=True, apply_left=True, apply_bottom=True, apply_top=True))
+    grid = perturbed(n, n, np.float64, 41)
+    out = {"f0": grid.copy(), "uw": np.array(uw), "omega": np.array(omega), "nsteps": np.array(nsteps)}
+    for s in range(nsteps):
+        ns["stream"](grid)
+        ns["bounce_back_choosen"](grid, uw, info)
+        rho, ux, uy = ns["caluculate_rho_ux_uy"](grid)
+        ns["collision"](grid, rho, ux, uy, omega)
+        if s + 1 in (1, 5, nsteps):
+            out["f_%d" % (s + 1)] = grid.copy()
+    np.savez_compressed(os.path.join(OUT, "table_sliding_lid_mpi.npz"), **out)
+    # obstacle_canal.py: the methods of obstacleWindTunnel, x periodic, bounce-back bottom / top, rectangular obstacle
+    path = "simulators/experimantal_flows/obstacle_canal.py"
+    import enum
+    states = enum.Enum("boundaryStates", "NONE BAUNCE_BACK BAUNCE_BACK_MOVING_WALL PERIODIC_BOUNDARY COMMUNICATE")
+    m = lift_methods(path, "obstacleWindTunnel", ("equilibrium", "stream", "bounce_back_choosen", "apply_obstacle",
+                                                   "caluculate_rho_ux_uy", "collision"),
+                     preset={"velocity_set": vs, "boundaryStates": states})
+    nx, ny, omega, nsteps = 24, 16, 0.9, 40
+    x0, x1, y0, y1 = 8, 12, 5, 9
+    BB, NO = states.BAUNCE_BACK, states.NONE
+    self = NS(grid=perturbed(nx, ny, np.float64, 43), relaxation=omega, uw=0.0, rho=None, ux=None, uy=None,
+              packed_info=NS(boundaries_info=NS(apply_right=NO, apply_left=NO, apply_bottom=BB, apply_top=BB)),
+              local_obstacle=NS(start_x=x0, end_x=x1, start_y=y0, end_y=y1,
+                                boundary_state=NS(apply_left=BB, apply_right=BB, apply_top=BB, apply_bottom=BB)))
+    self.equilibrium = lambda: m["equilibrium"](self)
+    out = {"f0": self.grid.copy(), "omega": np.array(omega), "nsteps": np.array(nsteps), "obstacle": np.array([x0, x1, y0, y1])}
+    for s in range(nsteps):
+        m["stream"](self)
+        m["bounce_back_choosen"](self)
+        m["caluculate_rho_ux_uy"](self)       # apply_obstacle zeroes ux / uy inside the obstacle; run() recomputes them right after (:273-274)
+        m["apply_obstacle"](self)
+        m["caluculate_rho_ux_uy"](self)
+        m["collision"](self)
+        if s + 1 in (1, 5, nsteps):
+            out["f_%d" % (s + 1)] = self.grid.copy()
+    np.savez_compressed(os.path.join(OUT, "table_obstacle_channel.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     gen_streaming()
@@ -240,6 +305,7 @@ def main():
     gen_cavity_opt0_collide()
     gen_shear_opt1_run()
     gen_simple_flows()
+    gen_table_flows()
     for n in sorted(os.listdir(OUT)):
         print("%-32s %8d bytes" % (n, os.path.getsize(os.path.join(OUT, n))))
 

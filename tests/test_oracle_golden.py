@@ -220,3 +220,42 @@ def test_bench_selfcheck_hashes_are_the_oracles(golden_dir):
     full = selfcheck.fields(64, 48, "float32")
     assert all(np.array_equal(a, b[5:25, 7:18]) for a, b in zip((rho, ux, uy), full))       # blocks are slices of the global fields
     assert all(np.array_equal(a.astype(np.float64), b) for a, b in zip(full, selfcheck.fields(64, 48, "float64")))   # exactly representable
+
+
+def _table_cases(golden_dir):
+    from latticeboltzmann_b200 import boundary_table as bt
+    g = np.load(os.path.join(golden_dir, "table_sliding_lid_mpi.npz"))
+    n = g["f0"].shape[1]
+    yield ("sliding_lid_mpi", g, bt.sliding_lid_mpi_table(n, n, float(g["uw"])),
+           lambda f: sf.sliding_lid_mpi_step(f, float(g["omega"]), float(g["uw"])))
+    h = np.load(os.path.join(golden_dir, "table_obstacle_channel.npz"))
+    x0, x1, y0, y1 = (int(v) for v in h["obstacle"])
+    yield ("obstacle_channel", h, bt.obstacle_channel_table(h["f0"].shape[1], h["f0"].shape[2], x0, x1, y0, y1),
+           lambda f: sf.obstacle_channel_step(f, float(h["omega"]), x0, x1, y0, y1))
+
+
+def test_boundary_tables_bitexact_vs_reference_functions(golden_dir):
+    """N4: slidingLidMPI.py's full-range bounce and obstacle_canal.py's rectangular obstacle.  Goldens come from the
+    reference's own functions / methods; the literal numpy restatement AND the symbolic per-cell table
+    (latticeboltzmann_b200/boundary_table.py, the form the kernel applies) both reproduce them bit for bit."""
+    for name, g, (cells, src, add), literal in _table_cases(golden_dir):
+        fa, fb = g["f0"].copy(), g["f0"].copy()
+        for s in range(1, int(g["nsteps"]) + 1):
+            literal(fa)
+            sf.table_step(fb, float(g["omega"]), cells, src, add)
+            if "f_%d" % s in g.files:
+                assert np.array_equal(fa, g["f_%d" % s]), (name, "literal", s)
+                assert np.array_equal(fb, g["f_%d" % s]), (name, "table", s)
+        assert 0 < len(cells) < fa.shape[1] * fa.shape[2] // 2          # O(perimeter) cells, not the lattice
+
+
+def test_symbolic_grid_rejects_what_a_table_cannot_hold():
+    from latticeboltzmann_b200.boundary_table import SymbolicGrid
+    g = SymbolicGrid(6, 5).stream()
+    g[7, :, -2] = g[5, :, -1] - 0.01
+    with pytest.raises(ValueError):
+        g[8, :, 1] = g[7, :, -2] + 0.01        # shifting an already shifted population: two roundings
+    with pytest.raises(TypeError):
+        g[1, 1, :] = 0.0
+    with pytest.raises(RuntimeError):
+        SymbolicGrid(4, 4).table()
