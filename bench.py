@@ -429,6 +429,35 @@ def main():
         except Exception as exc:
             extra["fp32_temporal_blocking"] = {"value": None, "error": repr(exc)}
 
+    # ---- in-place (AA pattern) variant of the single-step kernel: one buffer instead of the A/B pair (N = 1: one block)
+    if not args.no_extras and args.gpus == 1 and single and single.get("value"):
+        try:
+            latA = lb.Lattice(nx, ny, "cavity", omega=omega, u_wall=0.1, arith=args.arith, devices=local_rank, inplace=True)
+            latA.init_equilibrium()
+            latA.step(args.warmup)
+            latA.sync()
+            msA = latA.step_timed(args.steps)
+            latA.health()
+            digA = latA.checksum()
+            latA.close()
+            free0 = torch.cuda.mem_get_info(local_rank)[0]
+            latB = lb.Lattice(32768, 32768, "cavity", omega=omega_for_re(32768), u_wall=0.1, arith=args.arith, devices=local_rank, inplace=True)
+            used = free0 - torch.cuda.mem_get_info(local_rank)[0]
+            latB.init_equilibrium()
+            latB.step(4)
+            latB.sync()
+            msB = latB.step_timed(8)
+            latB.health()
+            latB.close()
+            gbsA = cells * BYTES_PER_CELL / (msA / args.steps * 1e-3) / 1e9
+            extra["inplace_aa"] = {"value": cells * args.steps / (msA * 1e-3) / 1e6, "unit": "MLUPS", "achieved_gbs": gbsA, "frac": gbsA / peak,
+                                   "relative_to_ab_single_step": (cells * args.steps / (msA * 1e-3) / 1e6) / single["value"],
+                                   "same_state_as_ab": ("%016x" % digA) == single["digest"],
+                                   "lattice_32768_device_gb": used / 1e9, "lattice_32768_mlups": 32768 * 32768 * 8 / (msB * 1e-3) / 1e6,
+                                   "note": "ONE copy of the populations (AA pattern, lb_create_ex LB_CREATE_INPLACE), 144 B per cell per step"}
+        except Exception as exc:
+            extra["inplace_aa"] = {"value": None, "error": repr(exc)}
+
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         from oracle import opt2_numpy

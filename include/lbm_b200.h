@@ -120,6 +120,14 @@ LB_API int lb_device_count(void);
 
 /* ---- (2) device-resident lattice ------------------------------------------------ */
 LB_API int lb_create(const lb_config *cfg, lb_lattice **out);
+/* lb_create with creation flags.
+ * LB_CREATE_INPLACE: ONE copy of the populations instead of the A/B pair (half the footprint: 32768^2 fp64 in
+ *   77 GB instead of 155 GB), advanced in place with the AA pattern -- even steps gather from the neighbours and
+ *   store each result back where its input came from, odd steps work on the cell's own slots -- at the same
+ *   144 B per cell per step and bit-identical to the A/B kernels.  One self-connected block, periodic / cavity
+ *   boundaries, single-step kernel only (no temporal blocking, probe, stream-only or host step).            */
+#define LB_CREATE_INPLACE 1
+LB_API int lb_create_ex(const lb_config *cfg, int flags, lb_lattice **out);
 LB_API int lb_destroy(lb_lattice *lat);
 /* Launch all work of this lattice on `cuda_stream` (a cudaStream_t / CUstream,
  * e.g. torch.cuda.current_stream().cuda_stream); 0 = the lattice's own stream. */

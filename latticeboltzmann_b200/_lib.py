@@ -51,6 +51,7 @@ SYMBOLS = {
     "lb_sizeof_export": (c_i64, []),
     "lb_device_count": (ctypes.c_int, []),
     "lb_create": (ctypes.c_int, [_P(LbConfig), _P(c_vp)]),
+    "lb_create_ex": (ctypes.c_int, [_P(LbConfig), ctypes.c_int, _P(c_vp)]),
     "lb_destroy": (ctypes.c_int, [c_vp]),
     "lb_set_stream": (ctypes.c_int, [c_vp, c_vp]),
     "lb_get_stream": (c_vp, [c_vp]),

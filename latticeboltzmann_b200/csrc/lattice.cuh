@@ -115,6 +115,8 @@ struct StepParams {
     T rho_in, rho_out;       // simple_flows Poiseuille (PoiseuilleFlow.py:134-135)
     int t2_rows, t2_tiles_l, t2_tiles_k;   // temporal blocking: rows per fused tile, tile grid over the deep interior
     int all_rim;             // 1: every cell takes the general (rim) path, no interior tiles
+    int bc;                  // boundary kind (BoundaryKind) for code that is not templated on it
+    int aa_swapped;          // in-place lattices: 1 while the single buffer is in the swapped layout (aa.cuh)
     int sys_scope;           // 1: some neighbour is on another device / process (system-scope fences)
     unsigned long long halo_timeout_ns;   // give up waiting for a neighbour's flag after this long
     // Byte offsets relative to a cell's own slot, precomputed on the host so that the kernel adds

@@ -2,6 +2,7 @@
 #include <cuda_runtime.h>
 #include <unistd.h>
 
+#include <algorithm>
 #include <atomic>
 #include <cstdarg>
 #include <cstdio>
@@ -16,6 +17,7 @@
 #include "step_kernel.cuh"
 #include "temporal.cuh"
 #include "resident.cuh"
+#include "aa.cuh"
 
 using namespace lbm;
 
@@ -64,6 +66,10 @@ struct lb_lattice {
     cudaEvent_t ev_tail = nullptr, ev_fin = nullptr;
     // decomposed host step: rim columns staged through pinned memory, begin/run handshake
     void *h_cols = nullptr, *d_cols = nullptr;
+    // in-place (AA pattern) lattice: one buffer, layout alternates natural / swapped (aa.cuh)
+    bool inplace = false, aa_swapped = false;
+    void *d_stash = nullptr, *d_stage = nullptr;
+    size_t stage_bytes = 0;
     // per-cell boundary table (LB_SF_TABLE)
     int *d_tab_cells = nullptr;
     long long *d_tab_src = nullptr;
@@ -116,7 +122,9 @@ StepParams<T> make_params(lb_lattice *L)
 {
     StepParams<T> p{};
     p.buf[0] = reinterpret_cast<T *>(L->base);
-    p.buf[1] = reinterpret_cast<T *>(L->base + L->buf_bytes);
+    p.buf[1] = L->inplace ? p.buf[0] : reinterpret_cast<T *>(L->base + L->buf_bytes);
+    p.bc = L->cfg.boundary;
+    p.aa_swapped = L->aa_swapped ? 1 : 0;
     p.ycol[0] = reinterpret_cast<T *>(L->base + L->ycol_off);
     p.ycol[1] = reinterpret_cast<T *>(L->base + L->ycol_off + L->ycol_bytes);
     p.frame = reinterpret_cast<T *>(L->base + L->frame_off);
@@ -288,7 +296,7 @@ constexpr long long T2_AUTO_MIN_TILES = 1024;
 
 bool temporal_ok(const lb_lattice *L)
 {
-    if (L->temporal == 1) return false;
+    if (L->temporal == 1 || L->inplace) return false;
     const bool eligible = L->cfg.boundary <= LB_CAVITY_XPERIODIC && L->cfg.lnx >= 16 && L->cfg.lny >= 16 && !L->d_series;
     if (!eligible) return false;
     if (L->temporal == 2) return true;
@@ -319,7 +327,7 @@ constexpr long long RESIDENT_MAX_CELLS = 1ll << 20;     // 2 x 72 B x 2^20 cells
 
 bool resident_ok(const lb_lattice *L)
 {
-    if (!L->use_resident || temporal_ok(L)) return false;
+    if (!L->use_resident || L->inplace || temporal_ok(L)) return false;
     if (L->cfg.lnx * L->cfg.lny > RESIDENT_MAX_CELLS) return false;
     for (int d = 0; d < LB_NUM_DIRS; ++d)
         if (!L->nbr[d].connected || L->nbr[d].base != L->base) return false;   // the wrap is index arithmetic: one self-connected block
@@ -394,6 +402,62 @@ int launch_resident(lb_lattice *L, int64_t nsteps)
     }
 }
 
+// ---- in-place (AA pattern) stepping, aa.cuh ------------------------------------------------------------------
+template <typename T, int BC, bool EXACT>
+int launch_aa_bc(lb_lattice *L)
+{
+    const StepParams<T> p = make_params<T>(L);
+    const int grid = p.tiles_l * p.tiles_k;
+    const T *stash = static_cast<const T *>(L->d_stash);
+    if (BC == BC_CAVITY) {
+        aa_corner_stash_kernel<T><<<1, 32, 0, L->stream>>>(p, static_cast<T *>(L->d_stash));
+        L->launches++;
+    }
+    if (L->aa_swapped)
+        aa_step_kernel<T, BC, EXACT, true><<<grid, TILE_L, 0, L->stream>>>(p, stash);
+    else
+        aa_step_kernel<T, BC, EXACT, false><<<grid, TILE_L, 0, L->stream>>>(p, stash);
+    L->launches++;
+    L->aa_swapped = !L->aa_swapped;
+    L->steps++;
+    return 0;
+}
+
+template <typename T>
+int launch_aa(lb_lattice *L)
+{
+    const bool exact = L->cfg.arith == LB_ARITH_EXACT;
+    switch (L->cfg.boundary) {
+    case LB_PERIODIC:
+        return exact ? launch_aa_bc<T, BC_PERIODIC, true>(L) : launch_aa_bc<T, BC_PERIODIC, false>(L);
+    case LB_CAVITY:
+        return exact ? launch_aa_bc<T, BC_CAVITY, true>(L) : launch_aa_bc<T, BC_CAVITY, false>(L);
+    case LB_CAVITY_XPERIODIC:
+        return exact ? launch_aa_bc<T, BC_CAVITY_XPERIODIC, true>(L) : launch_aa_bc<T, BC_CAVITY_XPERIODIC, false>(L);
+    default:
+        return lbm_fail(LB_ERR_INVALID, "in-place lattices support the periodic and cavity boundaries");
+    }
+}
+
+// device-side step counter of an in-place lattice (lb_health compares it with the host's)
+__global__ void aa_publish_kernel(DevState *st, unsigned long long steps)
+{
+    st->step = steps;
+    for (int d = 0; d < NUM_DIRS; ++d) st->flag_in[d] = steps;
+}
+
+int aa_step(lb_lattice *L, int64_t nsteps)
+{
+    for (int d = 0; d < LB_NUM_DIRS; ++d)
+        if (L->nbr[d].base != L->base) return lbm_fail(LB_ERR_STATE, "an in-place lattice is a single self-connected block");
+    if (L->d_series) return lbm_fail(LB_ERR_STATE, "the shear probe is not available on in-place lattices");
+    for (int64_t s = 0; s < nsteps; ++s)
+        if (int r = L->cfg.dtype == LB_F64 ? launch_aa<double>(L) : launch_aa<float>(L)) return r;
+    aa_publish_kernel<<<1, 1, 0, L->stream>>>(dev_state(L), (unsigned long long)L->steps);
+    LBM_CUDA(cudaGetLastError());
+    return 0;
+}
+
 int check_ready(lb_lattice *L)
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
@@ -420,7 +484,9 @@ int lb_device_count(void)
     return n;
 }
 
-int lb_create(const lb_config *cfg, lb_lattice **out)
+int lb_create(const lb_config *cfg, lb_lattice **out) { return lb_create_ex(cfg, 0, out); }
+
+int lb_create_ex(const lb_config *cfg, int flags, lb_lattice **out)
 {
     if (!cfg || !out) return lbm_fail(LB_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -444,8 +510,12 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     }
     if (lb_device_count() <= 0)
         return lbm_fail(LB_ERR_NO_DEVICE, "no CUDA device visible: liblbm_b200 has no CPU fallback");
+    if (flags & ~LB_CREATE_INPLACE) return lbm_fail(LB_ERR_INVALID, "unknown creation flags 0x%x", flags);
+    if ((flags & LB_CREATE_INPLACE) && (cfg->boundary > LB_CAVITY_XPERIODIC || cfg->lnx != cfg->gnx || cfg->lny != cfg->gny))
+        return lbm_fail(LB_ERR_INVALID, "in-place lattices: one block, periodic or cavity boundaries");
     lb_lattice *L = new lb_lattice();
     L->cfg = *cfg;
+    L->inplace = (flags & LB_CREATE_INPLACE) != 0;
     DeviceGuard guard(cfg->device);
     if (guard.err != cudaSuccess) {
         delete L;
@@ -457,7 +527,7 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
     L->pop_stride = (cfg->lnx + 2) * L->pitch;
     L->buf_bytes = (size_t)9 * L->pop_stride * L->elem;
     L->buf_bytes = (L->buf_bytes + 255) / 256 * 256;
-    L->ycol_off = 2 * L->buf_bytes;
+    L->ycol_off = (L->inplace ? 1 : 2) * L->buf_bytes;
     L->ycol_bytes = ((size_t)6 * (cfg->lnx + 2) * L->elem + 255) / 256 * 256;   // one ghost-column array per buffer
     L->frame_off = L->ycol_off + 2 * L->ycol_bytes;
     const size_t frame_bytes = ((size_t)frame_elems(cfg->lnx, L->pitch) * L->elem + 255) / 256 * 256;
@@ -468,7 +538,7 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
         const size_t want = L->total_bytes;
         delete L;
         cudaGetLastError();
-        return lbm_fail(LB_ERR_CUDA, "cudaMalloc(%zu bytes for two f buffers): %s", want, cudaGetErrorString(e));
+        return lbm_fail(LB_ERR_CUDA, "cudaMalloc(%zu bytes for the f buffer(s)): %s", want, cudaGetErrorString(e));
     }
     e = cudaStreamCreateWithFlags(&L->own_stream, cudaStreamNonBlocking);
     L->stream = L->own_stream;
@@ -480,6 +550,15 @@ int lb_create(const lb_config *cfg, lb_lattice **out)
         cudaGetLastError();
         lb_destroy(L);
         return lbm_fail(LB_ERR_CUDA, "lattice set-up failed: %s", cudaGetErrorString(e));
+    }
+    if (L->inplace) {
+        if (cudaMalloc(&L->d_stash, 4 * sizeof(double)) != cudaSuccess) {
+            cudaGetLastError();
+            lb_destroy(L);
+            return lbm_fail(LB_ERR_CUDA, "lattice set-up failed: stash allocation");
+        }
+        L->temporal = 1;
+        L->use_resident = false;
     }
     L->rows_per_tile = cfg->dtype == LB_F64 ? 4 : 8;     // measured optima
     if (const char *t = getenv("LBM_TEMPORAL")) L->temporal = (atoi(t) >= 0 && atoi(t) <= 2) ? atoi(t) : 0;
@@ -511,6 +590,8 @@ int lb_destroy(lb_lattice *L)
     if (L->d_tab_src) cudaFree(L->d_tab_src);
     if (L->d_tab_add) cudaFree(L->d_tab_add);
     if (L->d_tab_mask) cudaFree(L->d_tab_mask);
+    if (L->d_stash) cudaFree(L->d_stash);
+    if (L->d_stage) cudaFree(L->d_stage);
     if (L->h_cols) cudaFreeHost(L->h_cols);
     if (L->d_cols) cudaFree(L->d_cols);
     if (L->s_h2d) cudaStreamDestroy(L->s_h2d);
@@ -728,10 +809,45 @@ int lb_halo_refresh(lb_lattice *L)
     return 0;
 }
 
+// Download of rows [k_lo, k_hi) while an in-place lattice is in the swapped layout: gathered into natural order
+// slab by slab through a device staging array.
+static int aa_download_rows(lb_lattice *L, void *host, int64_t k_lo, int64_t k_hi)
+{
+    const size_t e = L->elem, row = (size_t)L->cfg.lny * e;
+    const int64_t slab = std::max<int64_t>(1, std::min<int64_t>(k_hi - k_lo, (int64_t)((256u << 20) / (9 * row))));
+    const size_t need = (size_t)9 * slab * row;
+    if (L->stage_bytes < need) {
+        if (L->d_stage) cudaFree(L->d_stage);
+        L->d_stage = nullptr;
+        L->stage_bytes = 0;
+        LBM_CUDA(cudaMalloc(&L->d_stage, need));
+        L->stage_bytes = need;
+    }
+    const int64_t rows_total = k_hi - k_lo;
+    for (int64_t a = k_lo; a < k_hi; a += slab) {
+        const int64_t b = std::min(k_hi, a + slab), n = (b - a) * L->cfg.lny;
+        if (L->cfg.dtype == LB_F64)
+            aa_gather_rows_kernel<double><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<double>(L), (double *)L->d_stage, (int)a, (int)b);
+        else
+            aa_gather_rows_kernel<float><<<grid_for(n, 256), 256, 0, L->stream>>>(make_params<float>(L), (float *)L->d_stage, (int)a, (int)b);
+        LBM_CUDA(cudaGetLastError());
+        L->launches++;
+        for (int i = 0; i < 9; ++i)
+            LBM_CUDA(cudaMemcpyAsync(static_cast<char *>(host) + ((size_t)i * rows_total + (size_t)(a - k_lo)) * row,
+                                     static_cast<char *>(L->d_stage) + (size_t)i * (size_t)n * e, (size_t)n * e, cudaMemcpyDeviceToHost, L->stream));
+        LBM_CUDA(cudaStreamSynchronize(L->stream));      // the staging array is reused by the next slab
+    }
+    return 0;
+}
+
 static int copy_f(lb_lattice *L, void *host, bool upload)
 {
     if (!L || !host) return lbm_fail(LB_ERR_INVALID, "null argument");
     LBM_ON_DEVICE(L);
+    if (L->inplace && L->aa_swapped) {
+        if (!upload) return aa_download_rows(L, host, 0, L->cfg.lnx);
+        L->aa_swapped = false;      // a whole-lattice upload (re)starts in the natural layout
+    }
     const size_t e = L->elem;
     char *cur = L->base + (size_t)L->cur * L->buf_bytes;
     const size_t row = (size_t)L->cfg.lny * e;
@@ -754,6 +870,7 @@ int lb_init_equilibrium(lb_lattice *L, const void *rho, const void *ux, const vo
 {
     if (!L) return lbm_fail(LB_ERR_INVALID, "null lattice");
     LBM_ON_DEVICE(L);
+    L->aa_swapped = false;          // in-place lattices restart in the natural layout
     const long long n = L->cfg.lnx * L->cfg.lny;
     const size_t bytes = (size_t)n * L->elem;
     struct Tmp {      // freed on every return path
@@ -814,6 +931,7 @@ int lb_step(lb_lattice *L, int64_t nsteps)
     if (nsteps < 0) return lbm_fail(LB_ERR_INVALID, "nsteps < 0");
     LBM_ON_DEVICE(L);
     const bool sf = L->cfg.boundary >= LB_SF_COUETTE;
+    if (L->inplace) return aa_step(L, nsteps);
     // Temporal blocking: two steps per pass over HBM (three launches per double step).
     if (temporal_ok(L)) {
         if (L->use_graph && nsteps >= 4 * GRAPH_DOUBLE) {
@@ -893,6 +1011,7 @@ int lb_step(lb_lattice *L, int64_t nsteps)
 int lb_stream_only(lb_lattice *L, int64_t nsteps)
 {
     if (int r = check_ready(L)) return r;
+    if (L->inplace) return lbm_fail(LB_ERR_STATE, "lb_stream_only is not available on in-place lattices");
     LBM_ON_DEVICE(L);
     for (int64_t s = 0; s < nsteps; ++s) {
         int r = L->cfg.dtype == LB_F64 ? launch_step<double>(L, false) : launch_step<float>(L, false);
@@ -1077,6 +1196,7 @@ int lb_step_host(lb_lattice *L, const void *host_in, void *host_out, int nslabs)
 {
     if (int r = check_ready(L)) return r;
     if (!host_in || !host_out) return lbm_fail(LB_ERR_INVALID, "null host buffer");
+    if (L->inplace) return lbm_fail(LB_ERR_STATE, "lb_step_host is not available on in-place lattices");
     bool self_ring = true;
     for (int d = 0; d < LB_NUM_DIRS; ++d)
         if (L->nbr[d].base != L->base) self_ring = false;
@@ -1184,6 +1304,10 @@ static int rows_io(lb_lattice *L, int64_t k_lo, int64_t k_hi, void *host, bool u
     if (!L || !host) return lbm_fail(LB_ERR_INVALID, "null argument");
     if (k_lo < 0 || k_hi > L->cfg.lnx || k_lo >= k_hi) return lbm_fail(LB_ERR_INVALID, "row range [%lld, %lld) outside the block", (long long)k_lo, (long long)k_hi);
     LBM_ON_DEVICE(L);
+    if (L->inplace && L->aa_swapped) {
+        if (upload) return lbm_fail(LB_ERR_STATE, "partial uploads need the natural layout (an even number of steps since the last upload)");
+        return aa_download_rows(L, host, k_lo, k_hi);
+    }
     if (int r = copy_rows(L, host, L->cur, k_lo, k_hi, upload, L->stream, k_lo, k_hi - k_lo)) return r;
     LBM_CUDA(cudaStreamSynchronize(L->stream));
     return 0;

@@ -58,6 +58,32 @@ __device__ __forceinline__ unsigned long long global_timer_ns()
     return t;
 }
 
+// ---- state access that is aware of the in-place (AA) layout, aa.cuh -------------------------------------
+// A lattice created with LB_CREATE_INPLACE keeps ONE buffer whose layout alternates between natural (f*_i(x) in
+// slot i of cell x) and swapped (f*_i(x) in slot opp(i) of cell x + c_i, or in its natural place where x + c_i
+// lies outside a wall).  Read-only consumers (moments, digest, downloads) go through aa_natural().
+__device__ __forceinline__ bool aa_outside_rt(int bc, int i, int k, int l, int lnx, int lny)
+{
+    if (bc == BC_PERIODIC) return false;
+    const bool walls = bc == BC_CAVITY;
+    return (cy_of(i) == 1 && l == 0) || (cy_of(i) == -1 && l == lny - 1) || (walls && cx_of(i) == 1 && k == 0) ||
+           (walls && cx_of(i) == -1 && k == lnx - 1);
+}
+__device__ __forceinline__ int wrap_idx(int a, int n) { return a < 0 ? a + n : (a >= n ? a - n : a); }
+
+// pre[i](k, l) = f*_i at cell (k, l), whichever layout the single buffer is in (see the file header)
+template <typename T>
+__device__ __forceinline__ T aa_natural(const StepParams<T> &p, const T *buf, int i, int k, int l)
+{
+    int kk = k, ll = l, slot = i;
+    if (p.aa_swapped && i != 0 && !aa_outside_rt(p.bc, opp_of(i), k, l, p.lnx, p.lny)) {
+        kk = wrap_idx(k + cx_of(i), p.lnx);
+        ll = wrap_idx(l + cy_of(i), p.lny);
+        slot = opp_of(i);
+    }
+    return __ldcg(buf + (long long)slot * p.pop_stride + (long long)(kk + 1) * p.pitch + (ll + PAD_L));
+}
+
 // Loads: rim tiles read ghost cells that a peer may have written during this
 // launch's lifetime, so they bypass the (non-coherent) L1.
 template <bool RIM, typename T>
@@ -470,7 +496,7 @@ __global__ void moments_kernel(const __grid_constant__ StepParams<T> p, T *__res
         const int k = (int)(t / p.lny), l = (int)(t % p.lny);
         T f[9];
 #pragma unroll
-        for (int i = 0; i < 9; ++i) f[i] = src[i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L)];
+        for (int i = 0; i < 9; ++i) f[i] = aa_natural<T>(p, src, i, k, l);
         T r, x, y;
         if (SF)
             sf_moments<T>(f, r, x, y);      // PoiseuilleFlow.py:49-53
@@ -534,7 +560,7 @@ __global__ void checksum_kernel(const __grid_constant__ StepParams<T> p, unsigne
         const int k = (int)(t / p.lny), l = (int)(t % p.lny);
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
-            const T v = src[i * p.pop_stride + (long long)(k + 1) * p.pitch + (l + PAD_L)];
+            const T v = aa_natural<T>(p, src, i, k, l);
             unsigned long long bits;
             if (sizeof(T) == 8)
                 bits = (unsigned long long)__double_as_longlong((double)v);

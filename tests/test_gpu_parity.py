@@ -393,3 +393,63 @@ def test_host_step_decomposed_bitexact(boundary, ndx, ndy):
     assert np.array_equal(lat.download(), ref)
     lat.health()
     lat.close()
+
+
+@pytest.mark.parametrize("dt", ["float64", "float32"])
+@pytest.mark.parametrize("boundary", ["periodic", "cavity", "cavity_xperiodic"])
+def test_inplace_aa_bitexact_vs_oracle(dt, boundary):
+    """LB_CREATE_INPLACE: ONE buffer advanced with the AA pattern.  Odd step counts leave the buffer in the swapped
+    layout -- downloads, row downloads, moments and the digest read through it -- and everything is bit-identical
+    to the oracle and to the A/B lattice, ragged / tiny / multi-tile shapes included."""
+    lb = require_gpu()
+    for nx, ny in SHAPES + [(300, 517)]:
+        if boundary != "periodic" and (ny < 2 or (boundary == "cavity" and nx < 2)):
+            continue
+        f0 = orc.perturbed_state(nx, ny, np.dtype(dt), seed=nx * 77 + ny)
+        run = (lambda f, n: orc.periodic_run(f, 1.7, n)) if boundary == "periodic" else \
+              (lambda f, n: orc.cavity_run(f, 1.7, n, 0.1, walls_lr=(boundary == "cavity")))
+        lat = lb.Lattice(nx, ny, boundary, omega=1.7, u_wall=0.1, dtype=dt, inplace=True)
+        ab = lb.Lattice(nx, ny, boundary, omega=1.7, u_wall=0.1, dtype=dt, temporal=1)
+        lat.upload(f0)
+        ab.upload(f0)
+        ref = f0.copy()
+        done = 0
+        for n in (7, 8, 21):                         # swapped, natural, swapped
+            lat.step(n - done)
+            ab.step(n - done)
+            run(ref, n - done)
+            done = n
+            assert np.array_equal(lat.download(), ref), (nx, ny, n)
+            assert lat.checksum() == ab.checksum(), (nx, ny, n)
+            for a, b in zip(lat.moments(), ab.moments()):
+                assert np.array_equal(a, b), (nx, ny, n)
+        if nx >= 5:
+            assert np.array_equal(lat.blocks[0].download_rows(1, 4), ref[:, 1:4])
+        lat.upload(ref)                              # an upload in the swapped state restarts in the natural layout
+        lat.step(2)
+        run(ref, 2)
+        assert np.array_equal(lat.download(), ref)
+        lat.health()
+        lat.close()
+        ab.close()
+
+
+def test_inplace_aa_long_run_and_restrictions():
+    lb = require_gpu()
+    nx, ny, omega = 96, 80, 1.7
+    ref = orc.init_equilibrium(nx, ny)
+    orc.cavity_run(ref, omega, 1001)
+    lat = lb.Lattice(nx, ny, "cavity", omega=omega, inplace=True)
+    lat.init_equilibrium()
+    lat.step(1001)
+    assert np.array_equal(lat.download(), ref)
+    lat.health()
+    with pytest.raises(lb.LbmError):
+        lat.stream_only(1)
+    with pytest.raises(lb.LbmError):
+        lat.blocks[0].upload_rows(0, 2, ref[:, 0:2].copy())        # swapped layout (1001 steps): partial uploads refused
+    lat.close()
+    with pytest.raises(lb.LbmError):
+        lb.Lattice(64, 64, "sf_couette", inplace=True)
+    with pytest.raises(lb.LbmError):
+        lb.Lattice(64, 64, "cavity", ndx=2, inplace=True)
