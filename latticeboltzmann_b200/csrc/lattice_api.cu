@@ -114,8 +114,8 @@ void drop_graph(lb_lattice *L)
 DevState *dev_state(lb_lattice *L) { return reinterpret_cast<DevState *>(L->base + L->state_off); }
 
 // Rows per fused tile.  64-row tiles recompute half as many level-(n+1) halo rows (2 per 64) but measured no
-// faster with the TMA-staged kernel (16384^2 fp64 EXACT: 87.1 vs 87.5 GLUPS), so 32 is the default.
-int t2_rows_for(const lb_lattice *L) { return L->t2_rows > 0 ? L->t2_rows : 32; }
+// faster with the TMA-staged fp64 kernel (16384^2 EXACT: 87.1 vs 87.5 GLUPS), so 32 is its default; fp32 gains 2 % (147.0 vs 143.9).
+int t2_rows_for(const lb_lattice *L) { return L->t2_rows > 0 ? L->t2_rows : (L->cfg.dtype == LB_F32 ? 64 : 32); }
 
 template <typename T>
 StepParams<T> make_params(lb_lattice *L)
@@ -1273,6 +1273,12 @@ int lb_probe_shear_enable(lb_lattice *L, int64_t l_global, const void *uy_k, int
     if (!L || !uy_k || capacity < 1) return lbm_fail(LB_ERR_INVALID, "bad argument");
     const int64_t l_local = l_global - L->cfg.y0;
     if (l_local < 0 || l_local >= L->cfg.lny) return lbm_fail(LB_ERR_INVALID, "probe row is not inside this block");
+    // The probe runs after every single step.  The stepping mode is a COLLECTIVE property of a decomposition, so a
+    // block that was told to advance two steps per pass is not silently downgraded (its neighbours would wait for
+    // frame flags it never posts): the caller switches every block to single steps first.
+    if (L->temporal == 2)
+        return lbm_fail(LB_ERR_STATE, "the shear probe needs single-step mode: lb_set_temporal(lat, 1, 0) on every block of the decomposition first");
+    if (L->inplace) return lbm_fail(LB_ERR_STATE, "the shear probe is not available on in-place lattices");
     LBM_ON_DEVICE(L);
     if (L->d_uyk) cudaFree(L->d_uyk);
     if (L->d_series) cudaFree(L->d_series);

@@ -80,6 +80,19 @@ __host__ __device__ inline int t2_tiles_over(long long lny) { return lny > 4 ? (
 #ifndef LBM_T2_STAGES
 #define LBM_T2_STAGES 3
 #endif
+// fp32 (16384^2 EXACT, GLUPS at 32- / 64-row tiles, profiles/r02_t2_variants.log): 3 stages x 2 CTAs 143.9 / 147.0,
+// 4 x 4 143.8 / 147.2, 6 x 2 128.7 / 131.9, 6 x 3 128.7 / 131.8, 8 x 2 104.7 / 107.6 -- deeper staging does not help:
+// at 36 B per cell per step the fp32 kernel is issue-bound (two collisions per cell per pass), not latency-bound.
+#ifndef LBM_T2_STAGES_F32
+#define LBM_T2_STAGES_F32 3
+#endif
+#ifndef LBM_T2_MINB_F32
+#define LBM_T2_MINB_F32 2
+#endif
+template <typename T>
+__host__ __device__ constexpr int t2_stages() { return sizeof(T) == 4 ? LBM_T2_STAGES_F32 : LBM_T2_STAGES; }
+template <typename T>
+__host__ __device__ constexpr int t2_minb() { return sizeof(T) == 4 ? LBM_T2_MINB_F32 : LBM_T2_MINB; }
 
 // Shared-memory ring of level-(n+1) rows, one barrier per row.  At iteration j (row j of level n+1 has just been
 // written) the level-(n+2) pull of row j-1 reads NW,SW from row j, N,S from row j-1 and NE,SE from row j-2, while
@@ -101,7 +114,7 @@ template <typename T>
 __host__ __device__ constexpr int t2_smem_bytes()
 {
     return (T2_RING_ROWS + (LBM_T2_ASYNC ? 9 : 0)) * T2_TILE * (int)sizeof(T) +
-           (LBM_T2_TMA ? LBM_T2_STAGES * (9 * t2_seg_elems<T>() * (int)sizeof(T) + 16) : 0);
+           (LBM_T2_TMA ? t2_stages<T>() * (9 * t2_seg_elems<T>() * (int)sizeof(T) + 16) : 0);
 }
 
 // cells closer than w to the perimeter (needs lnx, lny >= 2w)
@@ -380,7 +393,7 @@ __device__ __forceinline__ void bulk_g2s(unsigned dst_smem, const void *src, uns
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
 template <typename T, int BC, bool EXACT>
-__global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const __grid_constant__ StepParams<T> p)
+__global__ void __launch_bounds__(T2_TILE, t2_minb<T>()) t2_interior_kernel(const __grid_constant__ StepParams<T> p)
 {
     extern __shared__ __align__(128) unsigned char t2_smem_raw[];
     T *ring = reinterpret_cast<T *>(t2_smem_raw);               // [T2_RING_ROWS][T2_TILE]
@@ -411,7 +424,7 @@ __global__ void __launch_bounds__(T2_TILE, LBM_T2_MINB) t2_interior_kernel(const
     cp_async_commit();
 #endif
 #if LBM_T2_TMA
-    constexpr int AL = 16 / (int)sizeof(T), SEG = t2_seg_elems<T>(), NST = LBM_T2_STAGES;
+    constexpr int AL = 16 / (int)sizeof(T), SEG = t2_seg_elems<T>(), NST = t2_stages<T>();
     const T *stage = ring + T2_RING_ROWS * T2_TILE;             // [NST][9][SEG]
     const unsigned stage_s = smem_u32(stage);
     const unsigned full_s = stage_s + NST * 9 * SEG * (unsigned)sizeof(T);   // NST mbarriers, 8 bytes each

@@ -399,6 +399,8 @@ class Lattice:
         l_probe = self.ny // 2 if l_probe is None else l_probe
         uy_k = np.asarray(uy_k, self.dtype)
         self._probe = []
+        for b in self.blocks:           # the probe runs after every single step: the whole decomposition switches mode together
+            b.set_temporal(1)
         for r, b in enumerate(self.blocks):
             blk = self.decomp.block(r)
             if blk.y0 <= l_probe < blk.y0 + blk.lny:

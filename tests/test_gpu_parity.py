@@ -453,3 +453,24 @@ def test_inplace_aa_long_run_and_restrictions():
         lb.Lattice(64, 64, "sf_couette", inplace=True)
     with pytest.raises(lb.LbmError):
         lb.Lattice(64, 64, "cavity", ndx=2, inplace=True)
+
+
+def test_probe_switches_the_whole_decomposition_to_single_steps():
+    """The stepping mode is collective: enabling the shear probe on a forced two-steps-per-pass block is refused by
+    the C ABI (no silent per-block downgrade that would stall its neighbours); Lattice switches all blocks first."""
+    lb = require_gpu()
+    nx, ny = 64, 48
+    f0, uy_k = orc.shear_wave_init(nx, ny, a0=0.01)
+    lat = lb.Lattice(nx, ny, "periodic", omega=1.0, ndx=2, ndy=1, temporal=2)
+    assert all(b.temporal_active for b in lat.blocks)
+    with pytest.raises(lb.LbmError, match="single-step mode"):
+        lat.blocks[0].probe_shear_enable(ny // 2, uy_k[:32], 8)
+    lat.upload(f0)
+    lat.probe_shear_enable(uy_k, 8)
+    assert not any(b.temporal_active for b in lat.blocks)
+    lat.step(8)
+    ampl = lat.probe_shear_read(8)
+    ref = orc.periodic_run(f0.copy(), 1.0, 8, uy_k)
+    assert np.abs(ampl - ref).max() < 1e-14
+    lat.health()
+    lat.close()

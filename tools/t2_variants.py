@@ -14,6 +14,11 @@ sys.path.insert(0, ROOT)
 VDIR = os.path.join(ROOT, "latticeboltzmann_b200", "csrc", "variants")
 
 VARIANTS = {
+    "f32_3x2": ["LBM_T2_STAGES_F32=3", "LBM_T2_MINB_F32=2"],
+    "f32_6x2": ["LBM_T2_STAGES_F32=6", "LBM_T2_MINB_F32=2"],
+    "f32_6x3": ["LBM_T2_STAGES_F32=6", "LBM_T2_MINB_F32=3"],
+    "f32_4x4": ["LBM_T2_STAGES_F32=4", "LBM_T2_MINB_F32=4"],
+    "f32_8x2": ["LBM_T2_STAGES_F32=8", "LBM_T2_MINB_F32=2"],
     "res256": ["LBM_RES_THREADS=256"],
     "res512": ["LBM_RES_THREADS=512"],
     "res1024": ["LBM_RES_THREADS=1024"],
@@ -59,7 +64,8 @@ for (nx, ny, dt, bc) in ((70, 530, np.float64, "cavity"), (131, 1031, np.float64
 res["bit_exact"] = ok
 for rows in (32, 64):
     os.environ["LBM_T2_ROWS"] = str(rows)
-    lat = lb.Lattice(n, n, "cavity", omega=2000.0 / (0.6 * n + 1000.0), temporal=2)
+    lat = lb.Lattice(n, n, "cavity", omega=2000.0 / (0.6 * n + 1000.0), temporal=2,
+                     dtype=np.float32 if os.environ.get("LBM_VAR_DTYPE") == "f32" else np.float64)
     lat.init_equilibrium(); lat.step(6); lat.sync()
     best = min(lat.step_timed(steps) for _ in range(3))
     lat.health(); lat.close()
