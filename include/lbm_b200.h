@@ -211,10 +211,10 @@ LB_API int lb_set_halo_timeout_ms(lb_lattice *lat, int64_t ms);
 /* Time steps per pass over HBM.  2 = temporal blocking: lb_step advances pairs of steps with one read and
  * one write of the lattice (bit-identical results; periodic / cavity boundaries, blocks of at least 16 x 16
  * cells; odd remainders and everything else use the single-step kernel).  1 = always the single-step kernel.
- * 0 (default) = automatic: temporal blocking when the block offers at least 1024 fused tiles (about 2900^2
- * cells), else the single-step kernel.  The mode is a COLLECTIVE property of a decomposition: blocks that
+ * 0 (default) = automatic: temporal blocking when the block offers at least 512 fused tiles of 16 rows (about
+ * 1400^2 cells), else the single-step kernel.  The mode is a COLLECTIVE property of a decomposition: blocks that
  * exchange halos must all use the same mode (latticeboltzmann_b200.distributed decides it for the whole
- * world and sets 1 or 2 explicitly).  rows_per_tile > 0 overrides the fused tile height (default 32).
+ * world and sets 1 or 2 explicitly).  rows_per_tile > 0 overrides the fused tile height (default 16 or 32 by block size).
  * Environment override: LBM_TEMPORAL=0|1|2.                                                        */
 LB_API int lb_set_temporal(lb_lattice *lat, int steps_per_pass, int rows_per_tile);
 /* One phase (1, 2, 3) of a temporal-blocking double step, for drivers that run several blocks on ONE

@@ -52,6 +52,7 @@ struct DevState {
     unsigned long long fflag_in[NUM_DIRS]; // temporal blocking: level-(n+1) frame ghosts pushed by the neighbour in slot d
     unsigned long long grid_bar;           // resident multi-step kernel: arrivals at its grid barrier (monotone)
 };
+static_assert(sizeof(DevState) <= 256, "the allocation reserves 256 bytes for DevState");
 
 // ---- temporal blocking (two time steps per pass over HBM), temporal.cuh ----------------------------
 // The FRAME of a block = its cells closer than 3 cells to the perimeter.  Its level-(n+1) values live in a

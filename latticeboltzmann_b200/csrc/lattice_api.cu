@@ -115,7 +115,16 @@ DevState *dev_state(lb_lattice *L) { return reinterpret_cast<DevState *>(L->base
 
 // Rows per fused tile.  64-row tiles recompute half as many level-(n+1) halo rows (2 per 64) but measured no
 // faster with the TMA-staged fp64 kernel (16384^2 EXACT: 87.1 vs 87.5 GLUPS), so 32 is its default; fp32 gains 2 % (147.0 vs 143.9).
-int t2_rows_for(const lb_lattice *L) { return L->t2_rows > 0 ? L->t2_rows : (L->cfg.dtype == LB_F32 ? 64 : 32); }
+// Smaller lattices take 16-row tiles so that enough tiles remain to fill 148 SMs x 2 CTAs (profiles/r02_t2_rows_sweep.log,
+// r02_t2_small_sweep.log: 1536^2 45.4 (16 rows) vs 39.5 (32 rows) GLUPS; 4096^2 77.0 (32) vs 74.2 (16)).
+int t2_rows_for(const lb_lattice *L)
+{
+    if (L->t2_rows > 0) return L->t2_rows;
+    const long long tl = t2_tiles_over(L->cfg.lny);
+    auto tiles = [&](int rows) { return tl * ((L->cfg.lnx - 4 + rows - 1) / rows); };
+    if (L->cfg.dtype == LB_F32 && tiles(64) >= 1024) return 64;
+    return tiles(32) >= 1024 ? 32 : 16;
+}
 
 template <typename T>
 StepParams<T> make_params(lb_lattice *L)
@@ -290,9 +299,11 @@ int ensure_graph2(lb_lattice *L)
     return 0;
 }
 
-// Fused tiles a block must offer before the automatic mode prefers temporal blocking: below this the deep-
-// interior kernel cannot fill 148 SMs x 4 CTAs and the (latency-tuned, graph-replayed) single-step kernel wins.
-constexpr long long T2_AUTO_MIN_TILES = 1024;
+// Fused tiles (counted at 16 rows) a block must offer before the automatic mode prefers temporal blocking: below
+// this the deep-interior kernel cannot fill 148 SMs x 2 CTAs and the single-step kernel (graph replay) or the
+// resident kernel wins.  Measured crossover (profiles/r02_t2_small_sweep.log, GLUPS two-steps-per-pass vs single
+// step): 1024^2 32.5 vs 35.4 (39.5 resident), 1536^2 46.6 vs 38.7, 2048^2 57.7 vs 41.2.
+constexpr long long T2_AUTO_MIN_TILES = 512;
 
 bool temporal_ok(const lb_lattice *L)
 {
@@ -300,7 +311,7 @@ bool temporal_ok(const lb_lattice *L)
     const bool eligible = L->cfg.boundary <= LB_CAVITY_XPERIODIC && L->cfg.lnx >= 16 && L->cfg.lny >= 16 && !L->d_series;
     if (!eligible) return false;
     if (L->temporal == 2) return true;
-    const long long tiles = (long long)t2_tiles_over(L->cfg.lny) * ((L->cfg.lnx - 4 + 31) / 32);     // counted in 32-row tiles (decomposition.py)
+    const long long tiles = (long long)t2_tiles_over(L->cfg.lny) * ((L->cfg.lnx - 4 + 15) / 16);     // counted in 16-row tiles (decomposition.py)
     return tiles >= T2_AUTO_MIN_TILES;
 }
 

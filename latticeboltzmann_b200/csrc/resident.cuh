@@ -53,7 +53,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
     return v;
 }
 
-// All CTAs of the (cooperative, hence co-resident) grid: arrive, then wait until `target` arrivals were counted.
+// All CTAs of the (cooperative, hence co-resident) grid: arrive, then poll the counter until `target` arrivals were
+// counted.  (Measured alternative: the last arrival publishes a release word in a cache line of its own and the
+// others poll that -- one more serial hop, 300 x 200: 3.55 instead of 3.0 us per step -- so the counter is polled.)
 __device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned long long target)
 {
     __syncthreads();

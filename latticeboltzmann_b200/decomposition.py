@@ -76,8 +76,8 @@ class Decomposition:
 # ---- temporal blocking is a collective decision (csrc/temporal.cuh) -------------------------------------
 T2_MIN_EXTENT = 16            # a block needs at least 16 x 16 cells
 T2_TILE_COLS = 254            # output columns of a fused tile
-T2_TILE_ROWS = 32             # rows of a fused tile (library default)
-T2_AUTO_MIN_TILES = 1024      # automatic mode: fused tiles a block must offer to fill the GPU
+T2_TILE_ROWS = 16             # rows of the smallest fused tile the library picks
+T2_AUTO_MIN_TILES = 512       # automatic mode: fused tiles a block must offer to fill the GPU (about 1400^2 cells)
 
 
 def temporal_mode(blocks, boundary, requested=None):

@@ -87,10 +87,13 @@ def test_temporal_mode_decision():
     assert temporal_mode(small, "cavity", 2) == 2                   # forced
     assert temporal_mode(small, "sf_couette", 2) == 1               # simple_flows boundaries: single-step kernel
     assert temporal_mode(Decomposition(53, 47, 8, 1).blocks(), "cavity", 2) == 1      # 6-row slabs are ineligible
-    # the smallest block decides: 65536 x 2900 split in 2 columns of 1450 -> 6 x 2048 tiles each, fine;
-    # split 40 ways in x -> blocks of 1638 rows x 2900: 52 x 12 = 624 tiles -> single-step for everybody
+    # the smallest block decides (fused tiles counted at 16 rows x 254 columns, 512 needed): 65536 x 2900 split in 2
+    # columns of 1450 -> 6 x 4096 tiles each, fine; split 100 ways in x -> blocks of 655 rows x 2900: 41 x 12 = 492
+    # tiles -> single steps for everybody
     assert temporal_mode(Decomposition(65536, 2900, 1, 2).blocks(), "cavity") == 2
-    assert temporal_mode(Decomposition(65536, 2900, 40, 1).blocks(), "cavity") == 1
+    assert temporal_mode(Decomposition(65536, 2900, 100, 1).blocks(), "cavity") == 1
+    assert temporal_mode(Decomposition(1536, 1536).blocks(), "cavity") == 2       # measured crossover: 1536^2 wins, 1024^2 does not
+    assert temporal_mode(Decomposition(1024, 1024).blocks(), "cavity") == 1
 
 
 def test_temporal_blocking_eligibility_is_collective():
