@@ -138,26 +138,33 @@ def ncu_traffic_per_launch(arith, cells):
 
 
 def cpu_reference(nx_total, ny_total, omega, steps, warmup, cores=None):
-    """The reference-equivalent opt2 step (oracle/opt2_numpy.py) on the host cores: P processes,
-    each advancing one (bx, by) block of the lattice split over P ranks (the reference's
-    one-MPI-rank-per-block model, halo exchange omitted: mpirun / mpi4py are not installed).
+    """The reference's parallel cavity as it runs under mpirun (cavity_opt2.py:214-277), on the host cores:
+    P processes in a Cartesian grid, one block each with the reference's ghost layers, and per step
+    communicate() -> stream_and_bounce_back() (np.roll + numpy walls) -> compiled collide
+    (oracle/opt2_numpy.run_decomposed; mpirun / mpi4py are not installed, so the Sendrecv of communicate() are
+    shared-memory copies ordered by process barriers).  The lattice is the workload's own when it has at most
+    16384^2 cells, else a 16384^2 sample of it (bounded so that a step stays around a second).
     Returns (MLUPS, P, description)."""
     from oracle import opt2_numpy
     avail = len(os.sched_getaffinity(0))
-    p = cores or max(1, min(avail, 64))
-    # per-rank block of the real decomposition, bounded to 2048^2 cells so a step stays ~0.1-0.3 s
-    pd = 1
-    while pd * pd < p:
-        pd += 1
-    cap = int(os.environ.get("LBM_REF_BLOCK", "2048"))        # tests shrink the sample
-    bx = int(min(cap, max(64, nx_total // pd)))
-    by = int(min(cap, max(64, ny_total // pd)))
-    t = opt2_numpy.run_independent_blocks(p, bx, by, omega, warmup, steps)
-    mlups = p * bx * by * steps / t / 1e6
+    p = 1
+    while p * 2 <= (cores or max(1, min(avail, 64))):
+        p *= 2
+    pdx = 1
+    while pdx * pdx * 2 <= p:
+        pdx *= 2
+    pdy = p // pdx
+    cap = int(os.environ.get("LBM_REF_BLOCK", "4096"))        # per-process block edge; tests shrink it
+    nx = int(min(nx_total, 16384, cap * pdx))
+    ny = int(min(ny_total, 16384, cap * pdy))
+    t, _ = opt2_numpy.run_decomposed(pdx, pdy, nx, ny, omega, warmup, steps)
+    mlups = nx * ny * steps / t / 1e6
     cpu_reference.last_ms_per_step = t / steps * 1e3
-    desc = ("%d processes x %dx%d single-rank opt2 blocks = %d cells sampled of the %d-cell workload, %d steps; each block is "
-            "stepped like the reference (np.roll stream + numpy walls + compiled collide) but WITHOUT halo exchange between "
-            "the blocks (mpirun / mpi4py are not installed)" % (p, bx, by, p * bx * by, nx_total * ny_total, steps))
+    whole = nx == nx_total and ny == ny_total
+    desc = ("%s%dx%d lattice split over %dx%d processes (one block each, ghost layers and the four-way ghost exchange of "
+            "communicate() every step through shared memory, np.roll stream + numpy walls + compiled collide), %d steps"
+            % ("the whole " if whole else "a %d-cell sample of the %d-cell workload: " % (nx * ny, nx_total * ny_total),
+               nx, ny, pdx, pdy, steps))
     return mlups, p, desc
 
 
@@ -462,12 +469,12 @@ def main():
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         from oracle import opt2_numpy
         v, cores, sample = cpu_reference(nx, ny, omega, 3, 1)
-        cap = int(os.environ.get("LBM_REF_BLOCK", "2048"))
+        cap = min(2048, int(os.environ.get("LBM_REF_BLOCK", "2048")))
         one = opt2_numpy.run_independent_blocks(1, cap, cap, omega, 1, 2)
         cpu = {"value": v, "unit": "MLUPS", "cores": cores, "kind": "port", "sample": sample,
                "one_core_value": cap * cap * 2 / one / 1e6,
-               "note": "value: reference-structured opt2 step (np.roll stream + numpy walls + compiled collide) on all cores used; "
-                       "one_core_value: the same on 1 core"}
+               "note": "value: the reference's decomposed opt2 run (ghost exchange + np.roll stream + numpy walls + compiled collide) on "
+                       "all cores used; one_core_value: one undecomposed %dx%d block on 1 core" % (cap, cap)}
         if strip:
             rows, pre, post = strip
             ok = strip_check_vs_oracle(pre, post, omega, 0.1)

@@ -76,3 +76,94 @@ def run_independent_blocks(nproc, nx, ny, omega, warmup, steps):
         res = pool.map(_worker, [(nx, ny, omega, warmup, steps)] * nproc)
     return max(r[0] for r in res)
 
+
+
+# ---- the reference's decomposed run: one process per block, ghost exchange every step -------------------------
+def _local_layout(n, nd, p):
+    """cavity_opt2.py:231-258 along one axis: (global offset, real cells, ghost below?, ghost above?)."""
+    base = n // nd
+    real = base if p < nd - 1 else n - base * (nd - 1)
+    return p * base, real, p > 0, p < nd - 1
+
+
+def _decomposed_worker(rank, ndx, ndy, nx, ny, omega, warmup, steps, box, barrier, times, out):
+    import time
+    px, py = divmod(rank, ndy)                       # Create_cart row-major (cavity_opt2.py:225)
+    x0, rx, gxl, gxr = _local_layout(nx, ndx, px)
+    y0, ry, gyb, gyt = _local_layout(ny, ndy, py)
+    lnx, lny = rx + gxl + gxr, ry + gyb + gyt
+    f = orc.init_equilibrium(lnx, lny)               # :265-269, ghosts included
+    view = lambda r, name, shape: np.frombuffer(box[r][name], dtype=np.float64).reshape(shape)   # noqa: E731
+
+    def communicate():
+        # :191-199 -- x direction: real column 1 -> left neighbour's ghost -1, real column -2 -> right neighbour's ghost 0
+        if gxl:
+            view(rank, "to_left", (9, lny))[...] = f[:, 1, :]
+        if gxr:
+            view(rank, "to_right", (9, lny))[...] = f[:, -2, :]
+        barrier.wait()
+        if gxr:
+            f[:, -1, :] = view(rank + ndy, "to_left", (9, lny))
+        if gxl:
+            f[:, 0, :] = view(rank - ndy, "to_right", (9, lny))
+        barrier.wait()
+        # :201-210 -- y direction, x ghosts included (diagonals arrive in two hops)
+        if gyb:
+            view(rank, "to_bottom", (9, lnx))[...] = f[:, :, 1]
+        if gyt:
+            view(rank, "to_top", (9, lnx))[...] = f[:, :, -2]
+        barrier.wait()
+        if gyt:
+            f[:, :, -1] = view(rank + 1, "to_bottom", (9, lnx))
+        if gyb:
+            f[:, :, 0] = view(rank - 1, "to_top", (9, lnx))
+        barrier.wait()
+
+    def step():
+        communicate()
+        cavity_step(f, omega)                        # :276-277 on the local array, ghosts included, like the reference
+
+    for _ in range(warmup):
+        step()
+    barrier.wait()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    barrier.wait()
+    times[rank] = time.perf_counter() - t0
+    if out is not None:
+        g = np.frombuffer(out, dtype=np.float64).reshape(9, nx, ny)
+        g[:, x0:x0 + rx, y0:y0 + ry] = f[:, int(gxl):int(gxl) + rx, int(gyb):int(gyb) + ry]
+
+
+def run_decomposed(ndx, ndy, nx, ny, omega, warmup, steps, gather=False):
+    """The reference's parallel cavity as it runs under mpirun (cavity_opt2.py:214-277): ndx x ndy processes, one
+    block each (non-periodic Cartesian topology, ghost layers only towards existing neighbours, the last block of
+    an axis takes the remainder), per step communicate() -> stream_and_bounce_back() -> collide().  mpirun / mpi4py
+    are not installed, so the four Sendrecv of communicate() are copies through shared-memory mailboxes ordered by
+    process barriers.  Returns (seconds of the slowest process for `steps` steps, gathered field or None)."""
+    import multiprocessing as mp
+    orc.build()
+    ctx = mp.get_context("fork")
+    n = ndx * ndy
+    box = []
+    for r in range(n):
+        px, py = divmod(r, ndy)
+        _, rx, gxl, gxr = _local_layout(nx, ndx, px)
+        _, ry, gyb, gyt = _local_layout(ny, ndy, py)
+        lnx, lny = rx + gxl + gxr, ry + gyb + gyt
+        box.append({"to_left": ctx.RawArray("d", 9 * lny), "to_right": ctx.RawArray("d", 9 * lny),
+                    "to_bottom": ctx.RawArray("d", 9 * lnx), "to_top": ctx.RawArray("d", 9 * lnx)})
+    barrier = ctx.Barrier(n)
+    times = ctx.RawArray("d", n)
+    out = ctx.RawArray("d", 9 * nx * ny) if gather else None
+    procs = [ctx.Process(target=_decomposed_worker, args=(r, ndx, ndy, nx, ny, omega, warmup, steps, box, barrier, times, out))
+             for r in range(n)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join()
+        if p.exitcode != 0:
+            raise RuntimeError("a worker of the decomposed CPU run failed (exit code %s)" % p.exitcode)
+    g = np.frombuffer(out, dtype=np.float64).reshape(9, nx, ny).copy() if gather else None
+    return max(times), g

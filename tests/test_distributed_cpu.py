@@ -106,3 +106,18 @@ def test_temporal_blocking_eligibility_is_collective():
     rem = Decomposition(47, 64, 3, 1)            # 15, 15, 17: the remainder block alone would be eligible
     assert [b.lnx for b in rem.blocks()] == [15, 15, 17]
     assert not all(b.lnx >= 16 for b in rem.blocks())
+
+
+def test_cpu_baseline_decomposed_run_is_the_references():
+    """oracle/opt2_numpy.run_decomposed (what bench.py's reference arm times): the reference's own decomposition
+    and ghost exchange.  As in the reference y-splits reproduce the single-rank run bit for
+    bit, x-splits differ at the lid corners only (ghost column read instead of the opposite wall)."""
+    from oracle import opt2_numpy
+    nx, ny, steps = 23, 18, 12
+    ref = orc.init_equilibrium(nx, ny)
+    orc.cavity_run(ref, 1.7, steps)
+    for ndx, ndy in ((1, 1), (1, 2), (1, 3)):
+        _, g = opt2_numpy.run_decomposed(ndx, ndy, nx, ny, 1.7, 0, steps, gather=True)
+        assert np.array_equal(g, ref), (ndx, ndy)
+    _, g = opt2_numpy.run_decomposed(2, 2, nx, ny, 1.7, 0, steps, gather=True)
+    assert 0 < np.abs(g - ref).max() < 1e-3
