@@ -55,6 +55,8 @@ struct lb_lattice {
     bool use_resident = true;    // L2-resident single blocks: one cooperative launch for many steps (resident.cuh)
     unsigned long long grid_bar = 0;   // host mirror of DevState::grid_bar
     int resident_ctas = 0;       // co-resident CTAs of the resident kernel on this device (0: not queried yet)
+    int resident2_ctas = 0;      // the same for the two-steps-per-barrier variant
+    bool use_resident2 = true;
     // shear probe
     void *d_uyk = nullptr, *d_series = nullptr, *d_prod = nullptr;
     int64_t probe_capacity = 0, probe_l_local = -1, probe_step0 = 0;
@@ -358,6 +360,39 @@ int launch_resident_bc(lb_lattice *L, int64_t nsteps)
     }
     StepParams<T> p = make_params<T>(L);
     const bool probe = L->d_series != nullptr;
+    // Tiny lattices (all 16 x 32 tiles co-resident at one CTA per SM): two steps per grid barrier (resident2_kernel)
+    if constexpr (BC <= BC_CAVITY_XPERIODIC) if (L->use_resident2 && nsteps >= 2) {
+        auto kernel2 = resident2_kernel<T, BC, EXACT>;
+        if (!L->resident2_ctas) {
+            int per_sm = 0, sms = 0;
+            LBM_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel2, RES2_THREADS, 0));
+            LBM_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, L->cfg.device));
+            L->resident2_ctas = per_sm * sms > 0 ? per_sm * sms : -1;
+        }
+        const long long tiles = (long long)((p.lnx + RES2_TX - 1) / RES2_TX) * ((p.lny + RES2_TY - 1) / RES2_TY);
+        if (tiles + (probe ? 1 : 0) <= L->resident2_ctas) {
+            const int grid2 = (int)tiles + (probe ? 1 : 0);
+            while (nsteps >= 2) {
+                const int64_t chunk = (nsteps > (1 << 20) ? (1 << 20) : nsteps) & ~(int64_t)1;
+                ResidentArgs a{};
+                a.nsteps = chunk;
+                a.bar_base = L->grid_bar;
+                a.probe_l = probe ? (int)L->probe_l_local : -1;
+                a.uy_k = L->d_uyk;
+                a.series = L->d_series;
+                a.capacity = L->probe_capacity;
+                a.step0 = (unsigned long long)L->probe_step0;
+                a.prod = L->d_prod;
+                void *args[] = {&p, &a};
+                LBM_CUDA(cudaLaunchCooperativeKernel((void *)kernel2, dim3(grid2), dim3(RES2_THREADS), args, 0, L->stream));
+                L->grid_bar += (unsigned long long)grid2 * (unsigned long long)(chunk / 2);
+                L->launches++;
+                L->steps += chunk;
+                L->cur ^= (int)((chunk / 2) & 1);
+                nsteps -= chunk;
+            }
+        }
+    }
     const long long n = (long long)p.lnx * p.lny;
     long long workers = (n + RES_THREADS - 1) / RES_THREADS;
     if (workers > L->resident_ctas - (probe ? 1 : 0)) workers = L->resident_ctas - (probe ? 1 : 0);
@@ -574,6 +609,7 @@ int lb_create_ex(const lb_config *cfg, int flags, lb_lattice **out)
     L->rows_per_tile = cfg->dtype == LB_F64 ? 4 : 8;     // measured optima
     if (const char *t = getenv("LBM_TEMPORAL")) L->temporal = (atoi(t) >= 0 && atoi(t) <= 2) ? atoi(t) : 0;
     if (const char *t = getenv("LBM_RESIDENT")) L->use_resident = atoi(t) != 0;
+    if (const char *t = getenv("LBM_RESIDENT2")) L->use_resident2 = atoi(t) != 0;
     if (const char *t = getenv("LBM_T2_ROWS")) if (atoi(t) > 0) L->t2_rows = atoi(t);
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
@@ -1295,7 +1331,7 @@ int lb_probe_shear_enable(lb_lattice *L, int64_t l_global, const void *uy_k, int
     if (L->d_series) cudaFree(L->d_series);
     if (L->d_prod) cudaFree(L->d_prod);
     L->d_uyk = L->d_series = L->d_prod = nullptr;
-    LBM_CUDA(cudaMalloc(&L->d_prod, (size_t)2 * L->cfg.lnx * L->elem));
+    LBM_CUDA(cudaMalloc(&L->d_prod, (size_t)4 * L->cfg.lnx * L->elem));      // two passes x two levels (resident kernels)
     LBM_CUDA(cudaMalloc(&L->d_uyk, (size_t)L->cfg.lnx * L->elem));
     LBM_CUDA(cudaMalloc(&L->d_series, (size_t)capacity * L->elem));
     LBM_CUDA(cudaMemcpy(L->d_uyk, uy_k, (size_t)L->cfg.lnx * L->elem, cudaMemcpyHostToDevice));

@@ -29,6 +29,9 @@ namespace lbm {
 
 // Threads per CTA of the resident kernel.  Every CTA costs one serialised atomic arrival per barrier, so fewer,
 // fatter CTAs shorten the barrier; measured (300 x 200 / 512^2 simple_flows) in profiles/r02_small_lattices.log.
+#ifndef LBM_RES_RED_RELEASE
+#define LBM_RES_RED_RELEASE 1
+#endif
 #ifndef LBM_RES_THREADS
 #define LBM_RES_THREADS 512
 #endif
@@ -60,8 +63,14 @@ __device__ __forceinline__ void grid_barrier(unsigned long long *bar, unsigned l
 {
     __syncthreads();
     if (threadIdx.x == 0) {
+#if LBM_RES_RED_RELEASE
+        // one fire-and-forget release reduction: the CTA's stores (ordered before it by the bar.sync above, release is
+        // cumulative) become visible before the arrival counts, without a separate fence and without the atomic's return trip
+        asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(bar), "l"(1ull) : "memory");
+#else
         __threadfence();
         atomicAdd(bar, 1ull);
+#endif
         while (ld_acquire_gpu(bar) < target) {}
     }
     __syncthreads();
@@ -201,6 +210,124 @@ __global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_cons
         *(volatile unsigned int *)&st->cur = (unsigned int)par;
         *(volatile unsigned long long *)&st->step = done;
         for (int d = 0; d < NUM_DIRS; ++d) st->flag_in[d] = done;   // the caller refreshes the ghosts next (stream order)
+    }
+}
+
+// ---- two steps per grid barrier (tiny lattices) ---------------------------------------------------------------
+// Measured at 300 x 200 (one cell per thread): the grid barrier alone costs 1.36 us (three dependent L2 round
+// trips: arrival, counter update, poll), one step's load -> collide -> store chain 1.58 us; they add up (3.0 us).
+// Here a CTA owns a tile of RES2_TX x RES2_TY cells and advances it TWO steps per barrier: level n+1 of the tile
+// plus a one-cell halo (wrapped periodically -- the halo cells are real cells of the lattice, computed with their
+// own wall rules, which is exactly the reference's roll-then-overwrite semantics) goes to shared memory, level n+2
+// of the tile is gathered from there.  The halo is computed redundantly ((TX+2)(TY+2) = 612 cells for 512), so this
+// only pays while the barrier dominates: lattices whose tiles all fit the GPU at one CTA per SM.
+constexpr int RES2_TX = 16, RES2_TY = 32;
+constexpr int RES2_HX = RES2_TX + 2, RES2_HY = RES2_TY + 2, RES2_PITCH = RES2_HY + 2;
+constexpr int RES2_THREADS = 640;                   // >= RES2_HX * RES2_HY = 612: one level-(n+1) cell per thread
+static_assert(RES2_HX * RES2_HY <= RES2_THREADS && RES2_TX * RES2_TY <= RES2_THREADS, "one cell per thread at both levels");
+
+// level n+1: the tile's shared-memory copy (own cell at [r][c], halo included)
+template <typename T>
+struct SrcTile {
+    const T *lvl1;          // [9][RES2_HX][RES2_PITCH]
+    int r, c;
+    template <int I>
+    __device__ __forceinline__ T pull() const { return lvl1[(I * RES2_HX + (r - cx_of(I))) * RES2_PITCH + (c - cy_of(I))]; }
+    __device__ __forceinline__ T own(int i) const { return lvl1[(i * RES2_HX + r) * RES2_PITCH + c]; }
+};
+
+template <typename T, int BC, bool EXACT>
+__global__ void __launch_bounds__(RES2_THREADS) resident2_kernel(const __grid_constant__ StepParams<T> p, const ResidentArgs a)
+{
+    __shared__ T lvl1[9 * RES2_HX * RES2_PITCH];
+    __shared__ T red[256];
+    DevState *st = p.st;
+    const unsigned long long step = *(volatile unsigned long long *)&st->step;
+    int par = (int)*(volatile unsigned int *)&st->cur;
+    const bool probe = a.probe_l >= 0;
+    const int workers = (int)gridDim.x - (probe ? 1 : 0);
+    const bool reducer = probe && (int)blockIdx.x == workers;
+    const int tiles_l = (p.lny + RES2_TY - 1) / RES2_TY;
+    const int tk = (int)blockIdx.x / tiles_l, tl = (int)blockIdx.x - tk * tiles_l;
+    const int k0 = tk * RES2_TX, l0 = tl * RES2_TY;
+    const int txe = min(RES2_TX, p.lnx - k0), tye = min(RES2_TY, p.lny - l0);      // real extent of this tile
+    const int t = threadIdx.x;
+    unsigned long long bar = a.bar_base;
+    const T *uy_k = static_cast<const T *>(a.uy_k);
+    T *prod = static_cast<T *>(a.prod);             // [2 passes][2 levels][lnx]
+    T *series = static_cast<T *>(a.series);
+    const long long passes = a.nsteps / 2;
+
+    for (long long q = 0; q < passes; ++q) {
+        const T *__restrict__ src = p.buf[par];
+        T *__restrict__ dst = p.buf[par ^ 1];
+        if (!reducer) {
+            // level n -> n+1 on the tile and its one-cell halo
+            const int r = t / RES2_HY, c = t - r * RES2_HY;
+            if (r <= txe + 1 && c <= tye + 1 && t < RES2_HX * RES2_HY) {
+                const int k = wrap_idx(k0 - 1 + r, p.lnx), l = wrap_idx(l0 - 1 + c, p.lny);
+                const SrcWrap<T> sw{p, src, k, l};
+                T f[9];
+                pull9<T>(sw, f);
+                wall_rules<T, BC>(p, sw, f, k, l);
+                d2q9_collide<T, EXACT>(f, p.omega);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) lvl1[(i * RES2_HX + r) * RES2_PITCH + c] = f[i];
+                if (probe && l == a.probe_l && r >= 1 && r <= txe && c >= 1 && c <= tye) {
+                    T rr, x, y;
+                    d2q9_moments<T>(f, rr, x, y);
+                    prod[((q & 1) * 2 + 0) * p.lnx + k] = y * uy_k[k];
+                }
+            }
+            __syncthreads();
+            // level n+1 -> n+2 on the tile
+            const int r2 = t / RES2_TY + 1, c2 = t - (r2 - 1) * RES2_TY + 1;
+            if (t < RES2_TX * RES2_TY && r2 <= txe && c2 <= tye) {
+                const int k = k0 + r2 - 1, l = l0 + c2 - 1;
+                const SrcTile<T> ss{lvl1, r2, c2};
+                T g[9];
+                pull9<T>(ss, g);
+                wall_rules<T, BC>(p, ss, g, k, l);
+                d2q9_collide<T, EXACT>(g, p.omega);
+                T *dp = dst + (long long)(k + 1) * p.pitch + (l + PAD_L);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) dp[i * p.pop_stride] = g[i];
+                if (probe && l == a.probe_l) {
+                    T rr, x, y;
+                    d2q9_moments<T>(g, rr, x, y);
+                    prod[((q & 1) * 2 + 1) * p.lnx + k] = y * uy_k[k];
+                }
+            }
+        }
+        bar += gridDim.x;
+        grid_barrier(&st->grid_bar, bar);           // its leading __syncthreads also protects lvl1 for the next pass
+        if (reducer) {
+            for (int lev = 0; lev < 2; ++lev) {     // shear_wave_opt2.py:99 for both steps of the pass (tree of shear_probe_kernel)
+                T acc = T(0);
+                if (t < 256) {
+                    for (int k = t; k < p.lnx; k += 256) acc += __ldcg(prod + ((q & 1) * 2 + lev) * p.lnx + k);
+                    red[t] = acc;
+                }
+                __syncthreads();
+                for (int w = 128; w > 0; w >>= 1) {
+                    if (t < w) red[t] += red[t + w];
+                    __syncthreads();
+                }
+                if (t == 0) {
+                    const long long idx = (long long)(step + (unsigned long long)(2 * q + lev) + 1ull - a.step0) - 1;
+                    if (idx >= 0 && idx < a.capacity) series[idx] = red[0] * T(2) / T(p.gnx);
+                }
+                __syncthreads();
+            }
+        }
+        par ^= 1;
+    }
+
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const unsigned long long done = step + 2ull * (unsigned long long)passes;
+        *(volatile unsigned int *)&st->cur = (unsigned int)par;
+        *(volatile unsigned long long *)&st->step = done;
+        for (int d = 0; d < NUM_DIRS; ++d) st->flag_in[d] = done;
     }
 }
 
