@@ -144,7 +144,7 @@ __global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_cons
             for (long long t = t0; t < n; t += stride) {
                 const int k = (int)(t / p.lny), l = (int)(t - (long long)k * p.lny);
                 if (BC == BC_SF_POISEUILLE && !last && (k == 0 || k == p.lnx - 1)) continue;   // replaced by the pressure columns below
-                if (BC == BC_SF_TABLE && table_has(p.tab_mask, t)) continue;                     // a cell of the boundary table (below)
+                if (BC == BC_SF_TABLE && p.tab_n > 0 && table_has(p.tab_mask, t)) continue;                     // a cell of the boundary table (below)
                 const SrcWrap<T> sw{p, src, k, l};
                 T f[9];
                 pull9<T>(sw, f);
