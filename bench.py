@@ -465,6 +465,20 @@ def main():
         except Exception as exc:
             extra["inplace_aa"] = {"value": None, "error": repr(exc)}
 
+    # ---- the one workload the reference tree holds timings for: slidingLidMPI.py, 300^2, Re = 1000
+    if not args.no_extras and args.gpus == 1:
+        try:
+            from latticeboltzmann_b200.simulators import sliding_lid_mpi
+            sliding_lid_mpi.run(300, 20000, device=local_rank, verbose=False)                     # warm-up
+            _, _, secs = sliding_lid_mpi.run(300, 200000, device=local_rank, verbose=False)
+            extra["sliding_lid_mpi_300"] = {
+                "value": 300 * 300 * 200000 / secs / 1e6, "unit": "MLUPS", "us_per_step": secs / 200000 * 1e6, "steps": 200000,
+                "reference_published_mlups": {"1 rank": 4.5, "16 ranks": 95.6, "400 ranks (best)": 237.0},
+                "note": "simulators/simple_flows/slidingLidMPI.py (300x300 fluid nodes, Re=1000, uw=0.1; its 10^6-step wall times on bwUniCluster are "
+                        "the only timings in the reference tree, amdahldataviewer.py:40-49); here: per-cell boundary table + resident kernel, bit-identical"}
+        except Exception as exc:
+            extra["sliding_lid_mpi_300"] = {"value": None, "error": repr(exc)}
+
     cpu = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline:
         from oracle import opt2_numpy

@@ -130,6 +130,7 @@ struct StepParams {
     const long long *tab_src;
     const T *tab_add;
     const unsigned int *tab_mask;
+    const int *tab_rank;     // listed cells before each 32-cell word of tab_mask: table index of cell c = tab_rank[c >> 5] + popc(lower bits)
     int tab_n;
     NbrView<T> nbr[NUM_DIRS];
 };

@@ -77,6 +77,7 @@ struct lb_lattice {
     long long *d_tab_src = nullptr;
     void *d_tab_add = nullptr;
     unsigned int *d_tab_mask = nullptr;
+    int *d_tab_rank = nullptr;
     int tab_n = 0;
     bool host_begun = false;
 };
@@ -176,6 +177,7 @@ StepParams<T> make_params(lb_lattice *L)
     p.tab_src = L->d_tab_src;
     p.tab_add = static_cast<const T *>(L->d_tab_add);
     p.tab_mask = L->d_tab_mask;
+    p.tab_rank = L->d_tab_rank;
     p.tab_n = L->tab_n;
     p.sys_scope = 0;
     p.halo_timeout_ns = L->halo_timeout_ns;
@@ -637,6 +639,7 @@ int lb_destroy(lb_lattice *L)
     if (L->d_tab_src) cudaFree(L->d_tab_src);
     if (L->d_tab_add) cudaFree(L->d_tab_add);
     if (L->d_tab_mask) cudaFree(L->d_tab_mask);
+    if (L->d_tab_rank) cudaFree(L->d_tab_rank);
     if (L->d_stash) cudaFree(L->d_stash);
     if (L->d_stage) cudaFree(L->d_stage);
     if (L->h_cols) cudaFreeHost(L->h_cols);
@@ -719,20 +722,33 @@ int lb_set_boundary_table(lb_lattice *L, int64_t n, const int64_t *cells, const 
     if (L->cfg.boundary != LB_SF_TABLE) return lbm_fail(LB_ERR_STATE, "the lattice was not created with LB_SF_TABLE");
     const int64_t lnx = L->cfg.lnx, lny = L->cfg.lny, ncell = lnx * lny;
     if (n > ncell) return lbm_fail(LB_ERR_INVALID, "more table cells than lattice cells");
+    // entries sorted by cell, so that a cell's table index is its rank among the set bits of the mask
+    std::vector<int64_t> order((size_t)n);
+    for (int64_t j = 0; j < n; ++j) order[j] = j;
+    std::stable_sort(order.begin(), order.end(), [&](int64_t x, int64_t y) { return cells[x] < cells[y]; });
     std::vector<int> h_cells((size_t)n);
     std::vector<long long> h_src((size_t)n * 9);
+    std::vector<double> h_add((size_t)n * 9);
     std::vector<unsigned int> h_mask((size_t)(ncell + 31) / 32, 0u);
-    for (int64_t j = 0; j < n; ++j) {
+    for (int64_t jj = 0; jj < n; ++jj) {
+        const int64_t j = order[jj];
         if (cells[j] < 0 || cells[j] >= ncell) return lbm_fail(LB_ERR_INVALID, "table cell %lld is outside the lattice", (long long)cells[j]);
         if ((h_mask[cells[j] >> 5] >> (cells[j] & 31)) & 1u) return lbm_fail(LB_ERR_INVALID, "table cell %lld is listed twice", (long long)cells[j]);
         h_mask[cells[j] >> 5] |= 1u << (cells[j] & 31);
-        h_cells[j] = (int)cells[j];
+        h_cells[jj] = (int)cells[j];
         for (int i = 0; i < 9; ++i) {
             const int64_t e = src[9 * j + i];
             if (e < 0 || e >= 9 * ncell) return lbm_fail(LB_ERR_INVALID, "table source %lld is outside the state", (long long)e);
             const int64_t ch = e / ncell, k = (e - ch * ncell) / lny, l = e - ch * ncell - k * lny;
-            h_src[9 * j + i] = ch * L->pop_stride + (k + 1) * L->pitch + l + PAD_L;      // element offset inside a buffer
+            h_src[9 * jj + i] = ch * L->pop_stride + (k + 1) * L->pitch + l + PAD_L;      // element offset inside a buffer
+            h_add[9 * jj + i] = add[9 * j + i];
         }
+    }
+    std::vector<int> h_rank(h_mask.size());
+    int running = 0;
+    for (size_t w = 0; w < h_mask.size(); ++w) {
+        h_rank[w] = running;
+        running += __builtin_popcount(h_mask[w]);
     }
     LBM_ON_DEVICE(L);
     LBM_CUDA(cudaStreamSynchronize(L->stream));
@@ -740,17 +756,20 @@ int lb_set_boundary_table(lb_lattice *L, int64_t n, const int64_t *cells, const 
     if (L->d_tab_src) cudaFree(L->d_tab_src);
     if (L->d_tab_add) cudaFree(L->d_tab_add);
     if (L->d_tab_mask) cudaFree(L->d_tab_mask);
-    L->d_tab_cells = nullptr; L->d_tab_src = nullptr; L->d_tab_add = nullptr; L->d_tab_mask = nullptr;
+    if (L->d_tab_rank) cudaFree(L->d_tab_rank);
+    L->d_tab_cells = nullptr; L->d_tab_src = nullptr; L->d_tab_add = nullptr; L->d_tab_mask = nullptr; L->d_tab_rank = nullptr;
     L->tab_n = 0;
     LBM_CUDA(cudaMalloc(&L->d_tab_mask, h_mask.size() * sizeof(unsigned int)));
     LBM_CUDA(cudaMemcpy(L->d_tab_mask, h_mask.data(), h_mask.size() * sizeof(unsigned int), cudaMemcpyHostToDevice));
+    LBM_CUDA(cudaMalloc(&L->d_tab_rank, h_rank.size() * sizeof(int)));
+    LBM_CUDA(cudaMemcpy(L->d_tab_rank, h_rank.data(), h_rank.size() * sizeof(int), cudaMemcpyHostToDevice));
     if (n > 0) {
         LBM_CUDA(cudaMalloc(&L->d_tab_cells, (size_t)n * sizeof(int)));
         LBM_CUDA(cudaMalloc(&L->d_tab_src, (size_t)n * 9 * sizeof(long long)));
         LBM_CUDA(cudaMalloc(&L->d_tab_add, (size_t)n * 9 * sizeof(double)));
         LBM_CUDA(cudaMemcpy(L->d_tab_cells, h_cells.data(), (size_t)n * sizeof(int), cudaMemcpyHostToDevice));
         LBM_CUDA(cudaMemcpy(L->d_tab_src, h_src.data(), (size_t)n * 9 * sizeof(long long), cudaMemcpyHostToDevice));
-        LBM_CUDA(cudaMemcpy(L->d_tab_add, add, (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice));
+        LBM_CUDA(cudaMemcpy(L->d_tab_add, h_add.data(), (size_t)n * 9 * sizeof(double), cudaMemcpyHostToDevice));
     }
     L->tab_n = (int)n;
     return 0;

@@ -144,7 +144,10 @@ __global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_cons
             for (long long t = t0; t < n; t += stride) {
                 const int k = (int)(t / p.lny), l = (int)(t - (long long)k * p.lny);
                 if (BC == BC_SF_POISEUILLE && !last && (k == 0 || k == p.lnx - 1)) continue;   // replaced by the pressure columns below
-                if (BC == BC_SF_TABLE && p.tab_n > 0 && table_has(p.tab_mask, t)) continue;                     // a cell of the boundary table (below)
+                if (BC == BC_SF_TABLE && p.tab_n > 0 && table_has(p.tab_mask, t)) {               // a cell of the boundary table: its own gather
+                    table_cell<T>(p, src, dst, table_index<T>(p, t));
+                    continue;
+                }
                 const SrcWrap<T> sw{p, src, k, l};
                 T f[9];
                 pull9<T>(sw, f);
@@ -182,8 +185,6 @@ __global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_cons
                     prod[(s & 1) * p.lnx + k] = y * uy_k[k];
                 }
             }
-            if (BC == BC_SF_TABLE)
-                for (long long j = t0; j < p.tab_n; j += stride) table_cell<T>(p, src, dst, (int)j);
         }
         bar += gridDim.x;
         grid_barrier(&st->grid_bar, bar);

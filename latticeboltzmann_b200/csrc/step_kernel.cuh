@@ -510,16 +510,18 @@ __global__ void moments_kernel(const __grid_constant__ StepParams<T> p, T *__res
 
 // BC_SF_TABLE: cell j of the boundary table -- gather the nine populations from their tabulated pre-stream sources
 // (+ constant), collide, store (lattice.cuh: tab_*; latticeboltzmann_b200/boundary_table.py builds the table).
+// The table itself is read-only for the lifetime of a launch: __ldg keeps it in L1, so the index -> source -> value
+// chain costs one L2 round trip (the value), not three.
 template <typename T>
 __device__ __forceinline__ void table_cell(const StepParams<T> &p, const T *__restrict__ src, T *__restrict__ dst, int j)
 {
-    const int cell = p.tab_cells[j];
+    const int cell = __ldg(p.tab_cells + j);
     const int k = cell / p.lny, l = cell - k * p.lny;
     T f[9];
 #pragma unroll
     for (int i = 0; i < 9; ++i) {
-        const T v = __ldcg(src + p.tab_src[9 * (long long)j + i]);
-        const T c = p.tab_add[9 * (long long)j + i];
+        const T v = __ldcg(src + __ldg(p.tab_src + 9 * (long long)j + i));
+        const T c = __ldg(p.tab_add + 9 * (long long)j + i);
         f[i] = c == T(0) ? v : rn_add(v, c);      // x + 0 would turn -0 into +0; a plain copy must stay a copy
     }
     sf_collide<T>(f, p.omega);
@@ -527,7 +529,13 @@ __device__ __forceinline__ void table_cell(const StepParams<T> &p, const T *__re
 #pragma unroll
     for (int i = 0; i < 9; ++i) dp[i * p.pop_stride] = f[i];
 }
-__device__ __forceinline__ bool table_has(const unsigned int *mask, long long cell) { return (mask[cell >> 5] >> (cell & 31)) & 1u; }
+__device__ __forceinline__ bool table_has(const unsigned int *mask, long long cell) { return (__ldg(mask + (cell >> 5)) >> (cell & 31)) & 1u; }
+// index of a listed cell in the (cell-sorted) table
+template <typename T>
+__device__ __forceinline__ int table_index(const StepParams<T> &p, long long cell)
+{
+    return __ldg(p.tab_rank + (cell >> 5)) + __popc(__ldg(p.tab_mask + (cell >> 5)) & ((1u << (cell & 31)) - 1u));
+}
 
 // Per-step path of BC_SF_TABLE: after step_kernel streamed + collided EVERY cell periodically into the new current
 // buffer, the listed cells are recomputed from the previous buffer (still intact: A/B) with their table.

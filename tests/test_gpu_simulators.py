@@ -88,3 +88,21 @@ def test_checkpoint_restart_under_temporal_blocking(tmp_path, dt):
     assert np.array_equal(lat.download(), ref)
     lat.health()
     lat.close()
+
+
+def test_sliding_lid_mpi_driver():
+    """slidingLidMPI.py on one rank (base 40, 300 steps, its Re / uw / relaxation formula) == the literal numpy loop."""
+    require_gpu()
+    from latticeboltzmann_b200.simulators import sliding_lid_mpi
+    from oracle import simple_flows as sf
+    base, steps, re, uw = 40, 300, 1000.0, 0.1
+    ux, uy, _ = sliding_lid_mpi.run(base, steps, re, uw, verbose=False)
+    n = base + 2
+    f = sf.feq(np.ones((n, n)), np.zeros((n, n)), np.zeros((n, n)))
+    assert np.array_equal(f, sliding_lid_mpi.initial_state(n))
+    omega = (2 * re) / (6 * base * uw + re)
+    for _ in range(steps):
+        sf.sliding_lid_mpi_step(f, omega, uw)
+    _, rux, ruy = sf.moments(f)
+    assert np.array_equal(ux, rux[1:-1, 1:-1]) and np.array_equal(uy, ruy[1:-1, 1:-1])
+    assert np.abs(ux).max() > 1e-3          # the lid drags the fluid
