@@ -105,3 +105,19 @@ def test_pipelined_host_step_bitexact(boundary):
         else:
             orc.cavity_run(ref, 1.7, 3, 0.1, walls_lr=(boundary == "cavity"))
         assert np.array_equal(got, ref), nslabs
+
+
+def test_plain_c_client_runs_on_the_gpu(tmp_path):
+    """examples/c_abi_cavity.c (plain C over the ABI): A/B run, then the same run on an in-place lattice -- equal digests."""
+    import subprocess
+    require_gpu()
+    from latticeboltzmann_b200.build import build_native
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    so_dir = os.path.dirname(build_native())
+    exe = str(tmp_path / "c_abi_cavity")
+    subprocess.run(["gcc", "-std=c11", "-O2", "-Wall", "-Werror", "-I", os.path.join(root, "include"),
+                    os.path.join(root, "examples", "c_abi_cavity.c"), "-o", exe, "-L", so_dir, "-llbm_b200",
+                    "-Wl,-rpath," + so_dir], check=True)
+    r = subprocess.run([exe, "200", "150", "301"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "MLUPS" in r.stdout and "identical" in r.stdout
