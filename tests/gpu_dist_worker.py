@@ -16,7 +16,13 @@ from oracle import oracle as orc                       # noqa: E402
 
 def main():
     out, boundary, ndx, ndy, nx, ny, nsteps = sys.argv[1], sys.argv[2], *map(int, sys.argv[3:8])
-    rank, world, local = D.init_process_group("nccl")
+    # LBM_TEST_SHARE_GPUS=<n>: more ranks than GPUs -- ranks share devices (rank % n), the halo path is then CUDA IPC
+    # between PROCESSES on one device (system-scope flags, time-sliced contexts); NCCL refuses duplicate devices, so
+    # the rendezvous runs over gloo.
+    share = int(os.environ.get("LBM_TEST_SHARE_GPUS", "0"))
+    rank, world, local = D.init_process_group("gloo" if share else "nccl")
+    if share:
+        local = rank % share
     f0 = orc.perturbed_state(nx, ny, seed=33)
     # temporal=2: force the two-steps-per-pass mode (the automatic mode would pick the single-step kernel for
     # blocks this small), so that the level-(n+1) frame-ghost exchange crosses NVLink as well

@@ -1,5 +1,7 @@
-"""Multi-GPU parity (needs >= 2 GPUs; skipped otherwise): N ranks, one per GPU, in-kernel
-halo pushes over NVLink -> gathered field bit-identical to the single-rank oracle."""
+"""Multi-rank parity: N processes (one per GPU; with fewer GPUs than ranks the processes share the devices), in-kernel
+halo pushes into peer memory mapped with CUDA IPC (over NVLink between GPUs), device-side system-scope flags ->
+gathered field bit-identical to the single-rank oracle.  Never skipped: on a one-GPU box all ranks run on that GPU
+as separate processes, which exercises the same IPC mapping / flag protocol (time-sliced contexts)."""
 import json
 import os
 import socket
@@ -31,13 +33,16 @@ def _port():
                                               ("cavity", 2, 2), ("cavity", 4, 2), ("cavity", 8, 1)])
 def test_n_gpus_bit_identical_to_oracle(tmp_path, boundary, ndx, ndy):
     n = ndx * ndy
+    env = dict(os.environ)
     if _ngpu() < n:
-        pytest.skip("needs %d GPUs" % n)
+        # fewer GPUs than ranks: the ranks share the devices.  Still one PROCESS per block, so the exchange goes
+        # through CUDA IPC mappings and system-scope flags exactly as across GPUs -- only the wire (NVLink) is missing.
+        env["LBM_TEST_SHARE_GPUS"] = str(_ngpu())
     out = str(tmp_path / "verdict.json")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n),
            "--master-addr", "127.0.0.1", "--master-port", str(_port()),
            os.path.join(HERE, "gpu_dist_worker.py"), out, boundary, str(ndx), str(ndy), "301", "287", "40"]
-    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600, env=env)
     assert r.returncode == 0, r.stdout[-4000:]
     v = json.load(open(out))
     assert v["bit_exact"], v
