@@ -15,9 +15,9 @@
 //     kernel keeps c = C(s) between its passes (c' = C(SR(c))), i.e. one in-place collision first, fused passes,
 //     and a last pass without collision -- the stored state between lb_step calls is always the reference's s;
 //   * Poiseuille's pressure columns (PoiseuilleFlow.py:76-88: rows 0 and X rewritten from rows X-1 and 1 at the
-//     START of a step) are produced at the END of the previous pass by the threads that have just computed the
-//     cells of rows X-1 and 1 (they hold the nine post-collision populations in registers); the plain values of
-//     rows 0 and X, which nothing would ever read, are not computed in between.  Only the first pass of a launch
+//     START of a step) are produced at the END of the previous pass by the threads that own rows 0 and X: the plain
+//     values of those rows would never be read, so instead their threads recompute the new cells (X-1, l) / (1, l)
+//     (one ordinary cell update, the same dependent chain as everybody else) and store the pressure column.  Only the first pass of a launch
 //     rewrites the columns in a phase of its own, and the last pass leaves the plain rows, so the stored state
 //     between lb_step calls is the reference's.
 // Arithmetic, boundary rules and their order are the functions of step_kernel.cuh / temporal.cuh, so results are
@@ -142,8 +142,13 @@ __global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_cons
         const bool collide = !(a.couette_shift && last);
         if (!reducer) {
             for (long long t = t0; t < n; t += stride) {
-                const int k = (int)(t / p.lny), l = (int)(t - (long long)k * p.lny);
-                if (BC == BC_SF_POISEUILLE && !last && (k == 0 || k == p.lnx - 1)) continue;   // replaced by the pressure columns below
+                const int kown = (int)(t / p.lny), l = (int)(t - (long long)kown * p.lny);
+                // Poiseuille, all passes but the last: the plain values of rows 0 and X are never read (the pressure columns
+                // of the next step replace them), so their threads compute the pressure columns instead -- row 0 from the
+                // NEW cell (X-1, l), row X from the new cell (1, l), which they recompute themselves (one ordinary cell
+                // update, so every thread of the pass has the same dependent chain)
+                const bool pcol = BC == BC_SF_POISEUILLE && !last && (kown == 0 || kown == p.lnx - 1);
+                const int k = pcol ? (kown == 0 ? p.lnx - 2 : 1) : kown;
                 if (BC == BC_SF_TABLE && p.tab_n > 0 && table_has(p.tab_mask, t)) {               // a cell of the boundary table: its own gather
                     table_cell<T>(p, src, dst, table_index<T>(p, t));
                     continue;
@@ -162,23 +167,18 @@ __global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_cons
                     else
                         d2q9_collide<T, EXACT>(f, p.omega);
                 }
-                T *dp = dst + c;
-#pragma unroll
-                for (int i = 0; i < 9; ++i) dp[i * p.pop_stride] = f[i];
-                if (BC == BC_SF_POISEUILLE && !last && (k == 1 || k == p.lnx - 2)) {
-                    // PoiseuilleFlow.py:78-88 for the NEXT step, from this cell's new populations (== sf_pressure_cell)
+                if (pcol) {
+                    // PoiseuilleFlow.py:78-88 for the NEXT step, from the new populations of cell (k, l) (== sf_pressure_cell)
                     T e[9], en[9], rho, ux, uy;
                     sf_moments<T>(f, rho, ux, uy);
                     sf_equilibrium<T>(rho, ux, uy, e);
-#pragma unroll 1
-                    for (int side = 0; side < 2; ++side) {
-                        if (k != (side == 0 ? p.lnx - 2 : 1)) continue;
-                        sf_equilibrium<T>(side == 0 ? p.rho_in : p.rho_out, ux, uy, en);
-                        T *d = dst + (long long)((side == 0 ? 0 : p.lnx - 1) + 1) * p.pitch + (l + PAD_L);
+                    sf_equilibrium<T>(kown == 0 ? p.rho_in : p.rho_out, ux, uy, en);
 #pragma unroll
-                        for (int i = 0; i < 9; ++i) d[i * p.pop_stride] = rn_add(en[i], rn_sub(f[i], e[i]));
-                    }
+                    for (int i = 0; i < 9; ++i) f[i] = rn_add(en[i], rn_sub(f[i], e[i]));
                 }
+                T *dp = dst + (long long)(kown + 1) * p.pitch + (l + PAD_L);
+#pragma unroll
+                for (int i = 0; i < 9; ++i) dp[i * p.pop_stride] = f[i];
                 if (probe && l == a.probe_l) {
                     T r, x, y;
                     d2q9_moments<T>(f, r, x, y);
