@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_cons
     if (a.couette_shift) {              // c = C(s): in place on the current buffer
         if (!reducer)
             for (long long t = t0; t < n; t += stride) {
-                const int k = (int)(t / p.lny), l = (int)(t - (long long)k * p.lny);
+                const int k = (int)((unsigned)t / (unsigned)p.lny), l = (int)t - k * p.lny;      // at most 2^20 cells: 32-bit division
                 T *q = p.buf[par] + (long long)(k + 1) * p.pitch + (l + PAD_L);
                 T f[9];
 #pragma unroll
@@ -142,7 +142,7 @@ __global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_cons
         const bool collide = !(a.couette_shift && last);
         if (!reducer) {
             for (long long t = t0; t < n; t += stride) {
-                const int kown = (int)(t / p.lny), l = (int)(t - (long long)kown * p.lny);
+                const int kown = (int)((unsigned)t / (unsigned)p.lny), l = (int)t - kown * p.lny;      // at most 2^20 cells: 32-bit division
                 // Poiseuille, all passes but the last: the plain values of rows 0 and X are never read (the pressure columns
                 // of the next step replace them), so their threads compute the pressure columns instead -- row 0 from the
                 // NEW cell (X-1, l), row X from the new cell (1, l), which they recompute themselves (one ordinary cell
