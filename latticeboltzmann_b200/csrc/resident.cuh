@@ -221,7 +221,9 @@ __global__ void __launch_bounds__(RES_THREADS) resident_kernel(const __grid_cons
 // plus a one-cell halo (wrapped periodically -- the halo cells are real cells of the lattice, computed with their
 // own wall rules, which is exactly the reference's roll-then-overwrite semantics) goes to shared memory, level n+2
 // of the tile is gathered from there.  The halo is computed redundantly ((TX+2)(TY+2) = 612 cells for 512), so this
-// only pays while the barrier dominates: lattices whose tiles all fit the GPU at one CTA per SM.
+// only pays while the barrier dominates: lattices whose tiles all fit the GPU at one CTA per SM.  (Measured: letting a
+// CTA walk through several tiles per pass on larger L2-resident lattices does not help -- cavity 512^2 7.09 vs 6.96 us
+// per step, 1024^2 28.7 vs 26.1 -- at 20 warps per SM the two dependent phases per tile are latency-bound.)
 constexpr int RES2_TX = 16, RES2_TY = 32;
 constexpr int RES2_HX = RES2_TX + 2, RES2_HY = RES2_TY + 2, RES2_PITCH = RES2_HY + 2;
 constexpr int RES2_THREADS = 640;                   // >= RES2_HX * RES2_HY = 612: one level-(n+1) cell per thread
