@@ -55,12 +55,9 @@ __host__ __device__ inline int t2_tiles_over(long long lny) { return lny > 4 ? (
 // WITHOUT prefetch at 64 registers / 4 CTAs (32 warps): 78.1; 128-thread tiles: 60-61; 3-slot ring, two barriers per
 // row: 49-63.  Round 2 (tools/t2_variants.py, profiles/r02_t2_variants.log): LBM_T2_COMPACT_RING keeps only the rows
 // each ring population still needs (18 instead of 24 population-rows): 78.6 -> 80.3 (32-row tiles) / 80.8 (64-row
-// tiles); LBM_T2_ASYNC stages the NEXT row's nine level-n sources with per-thread 8-byte cp.async (LDGSTS): 60.6 --
-// the LSU/MIO path of 9 x 8-byte LDGSTS per cell costs more than the latency it hides (ncu: mio_throttle 5.6 per
-// issue), so it stays off; sector-aligned tile seams (W=252): 78.4, no gain.
-#ifndef LBM_T2_ASYNC
-#define LBM_T2_ASYNC 0
-#endif
+// tiles); staging the NEXT row's nine level-n sources with per-thread 8-byte cp.async (LDGSTS): 60.6 -- the LSU/MIO
+// path of 9 x 8-byte LDGSTS per cell costs more than the latency it hides (ncu: mio_throttle 5.6 per issue), so that
+// variant was removed again; sector-aligned tile seams (W=252): 78.4, no gain.
 #ifndef LBM_T2_COMPACT_RING
 #define LBM_T2_COMPACT_RING 1
 #endif
@@ -113,7 +110,7 @@ __host__ __device__ constexpr int t2_seg_elems() { return T2_TILE + 16 / (int)si
 template <typename T>
 __host__ __device__ constexpr int t2_smem_bytes()
 {
-    return (T2_RING_ROWS + (LBM_T2_ASYNC ? 9 : 0)) * T2_TILE * (int)sizeof(T) +
+    return T2_RING_ROWS * T2_TILE * (int)sizeof(T) +
            (LBM_T2_TMA ? t2_stages<T>() * (9 * t2_seg_elems<T>() * (int)sizeof(T) + 16) : 0);
 }
 
@@ -356,14 +353,6 @@ __global__ void __launch_bounds__(TILE_L) t2_frame2_kernel(const __grid_constant
 // that shift in y go through a shared-memory ring (neighbouring threads consume them), the three that do not
 // (rest, E, W: consumed by the SAME thread one row later / earlier) stay in registers.
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
-template <int BYTES>
-__device__ __forceinline__ void cp_async(unsigned dst_smem, const void *src)
-{
-    asm volatile("cp.async.ca.shared.global [%0], [%1], %2;" ::"r"(dst_smem), "l"(src), "n"(BYTES) : "memory");
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-
 // mbarrier + bulk-async copy (TMA unit, no tensor map: plain 1-D copies)
 __device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
 {
@@ -412,17 +401,6 @@ __global__ void __launch_bounds__(T2_TILE, t2_minb<T>()) t2_interior_kernel(cons
     const char *sp = reinterpret_cast<const char *>(src + (long long)k0 * p.pitch + (lc + PAD_L));        // row k0-1
     T *dp = dst + (long long)(k0 + 1) * p.pitch + (lc + PAD_L);                                           // row k0
     T rest_m1 = T(0), e_m1 = T(0), e_m2 = T(0);                 // level n+1: rest of row j-1, E of rows j-1 and j-2
-#if LBM_T2_ASYNC
-    // Stage of this thread's nine level-n sources for the NEXT row: written by cp.async while the current row is
-    // collided twice, read back by the SAME thread (no barrier: cp.async.wait_group covers a thread's own copies).
-    T *stage = ring + T2_RING_ROWS * T2_TILE + t;
-    const unsigned stage_s = smem_u32(stage);
-    if (have1) {
-#pragma unroll
-        for (int i = 0; i < 9; ++i) cp_async<(int)sizeof(T)>(stage_s + i * T2_TILE * (int)sizeof(T), sp + p.ld_off[i]);
-    }
-    cp_async_commit();
-#endif
 #if LBM_T2_TMA
     constexpr int AL = 16 / (int)sizeof(T), SEG = t2_seg_elems<T>(), NST = t2_stages<T>();
     const T *stage = ring + T2_RING_ROWS * T2_TILE;             // [NST][9][SEG]
@@ -457,9 +435,6 @@ __global__ void __launch_bounds__(T2_TILE, t2_minb<T>()) t2_interior_kernel(cons
     for (int j = k0 - 1; j <= k1; ++j) {
         sp += row_bytes;
         T f[9];
-#if LBM_T2_ASYNC
-        cp_async_wait_all();
-#endif
 #if LBM_T2_TMA
         mbar_wait(full_s + 8u * st_cur, st_par);
 #endif
@@ -467,14 +442,6 @@ __global__ void __launch_bounds__(T2_TILE, t2_minb<T>()) t2_interior_kernel(cons
 #if LBM_T2_TMA
 #pragma unroll
             for (int i = 0; i < 9; ++i) f[i] = stage[(st_cur * 9 + i) * SEG + ((lc0 - cy_of(i)) & (AL - 1)) + t];
-#elif LBM_T2_ASYNC
-#pragma unroll
-            for (int i = 0; i < 9; ++i) f[i] = stage[i * T2_TILE];
-            if (j < k1) {
-#pragma unroll
-                for (int i = 0; i < 9; ++i) cp_async<(int)sizeof(T)>(stage_s + i * T2_TILE * (int)sizeof(T), sp + p.ld_off[i]);
-            }
-            cp_async_commit();
 #else
             interior_load<T>(p, sp - row_bytes, f);
 #endif
@@ -530,9 +497,6 @@ __global__ void __launch_bounds__(T2_TILE, t2_minb<T>()) t2_interior_kernel(cons
         rest_m1 = rest_0;
         s3 = s3 == 2 ? 0 : s3 + 1;
     }
-#if LBM_T2_ASYNC
-    cp_async_wait_all();
-#endif
 }
 
 }  // namespace lbm

@@ -26,12 +26,9 @@ VARIANTS = {
     "tma2": ["LBM_T2_TMA=1", "LBM_T2_STAGES=2", "LBM_T2_MINB=3"],
     "tma4": ["LBM_T2_TMA=1", "LBM_T2_STAGES=4", "LBM_T2_MINB=2"],
     "tma3": ["LBM_T2_TMA=1", "LBM_T2_STAGES=3", "LBM_T2_MINB=2"],
-    "r1": ["LBM_T2_ASYNC=0", "LBM_T2_COMPACT_RING=0"],                                 # round-1 shipped kernel
-    "compact": ["LBM_T2_ASYNC=0", "LBM_T2_COMPACT_RING=1"],
-    "async4": ["LBM_T2_ASYNC=1", "LBM_T2_COMPACT_RING=1", "LBM_T2_MINB=4"],
-    "async3": ["LBM_T2_ASYNC=1", "LBM_T2_COMPACT_RING=0", "LBM_T2_MINB=3"],
-    "async4_al": ["LBM_T2_ASYNC=1", "LBM_T2_COMPACT_RING=1", "LBM_T2_MINB=4", "LBM_T2_W=252", "LBM_T2_S=0", "LBM_T2_OFF=2"],
-    "r1_al": ["LBM_T2_ASYNC=0", "LBM_T2_COMPACT_RING=0", "LBM_T2_W=252", "LBM_T2_S=0", "LBM_T2_OFF=2"],
+    "r1": ["LBM_T2_TMA=0", "LBM_T2_COMPACT_RING=0", "LBM_T2_MINB=4"],                # round-1 shipped kernel (direct loads)
+    "compact": ["LBM_T2_TMA=0", "LBM_T2_COMPACT_RING=1", "LBM_T2_MINB=4"],
+    "r1_al": ["LBM_T2_TMA=0", "LBM_T2_COMPACT_RING=0", "LBM_T2_MINB=4", "LBM_T2_W=252", "LBM_T2_S=0", "LBM_T2_OFF=2"],
 }
 
 
