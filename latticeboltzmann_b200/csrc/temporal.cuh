@@ -58,6 +58,12 @@ __host__ __device__ inline int t2_tiles_over(long long lny) { return lny > 4 ? (
 // tiles); staging the NEXT row's nine level-n sources with per-thread 8-byte cp.async (LDGSTS): 60.6 -- the LSU/MIO
 // path of 9 x 8-byte LDGSTS per cell costs more than the latency it hides (ncu: mio_throttle 5.6 per issue), so that
 // variant was removed again; sector-aligned tile seams (W=252): 78.4, no gain.
+// Launch order / walking direction (profiles/r02_t2_order_sweep.log): vertically adjacent tiles walking towards their
+// common seam (odd bands top-down) so that the shared halo rows are read at the same time and hit L2, with bands
+// launched in groups of 1 / 2 / 4 / 8 / 16 / 32 / all: 86.7 / 83.6 / 85.8 / 85.6 / 83.4 / 84.1 / 75.6 vs 86.3 GLUPS for the
+// plain band-major upward walk at 16384^2 (4096^2: 76.3 ... 69.6 vs 75.9) -- no gain (the kernel is not limited by
+// the 3.5 % of redundant reads alone), column-major order is 13 % slower; removed again.  Tile heights 24 .. 48 are
+// within 1 % of each other at 3072^2 .. 8192^2 (profiles/r02_t2_rows_sweep.log).
 #ifndef LBM_T2_COMPACT_RING
 #define LBM_T2_COMPACT_RING 1
 #endif
@@ -407,14 +413,18 @@ __global__ void __launch_bounds__(T2_TILE, t2_minb<T>()) t2_interior_kernel(cons
     const unsigned stage_s = smem_u32(stage);
     const unsigned full_s = stage_s + NST * 9 * SEG * (unsigned)sizeof(T);   // NST mbarriers, 8 bytes each
     const int lc0 = lt * T2_W + T2_S - T2_OFF;                  // column of thread 0
+    // The last tile of a row band is usually narrower than the others (16384 columns: 124 of 254; 4096: 28 of 254):
+    // it copies only the 16-byte units its level-(n+1) threads (columns <= lny - 2) read.
+    const int ncols = min(T2_TILE, p.lny - 1 - lc0);
+    const unsigned seg_bytes = (unsigned)(((ncols + AL - 1 + AL - 1) / AL) * AL * (int)sizeof(T));      // <= SEG elements
     // stage `st` <- the nine source segments of level-(n+1) row `row`: population i from row (row - cx_i), columns
     // from (lc0 - cy_i) rounded down to a 16-byte unit
     auto stage_row = [&](int row, int st) {
-        mbar_expect_tx(full_s + 8u * st, 9u * SEG * (unsigned)sizeof(T));
+        mbar_expect_tx(full_s + 8u * st, 9u * seg_bytes);
 #pragma unroll
         for (int i = 0; i < 9; ++i) {
             const T *g = src + (long long)i * p.pop_stride + (long long)(row - cx_of(i) + 1) * p.pitch + (PAD_L + (((lc0 - cy_of(i)) / AL) * AL));
-            bulk_g2s(stage_s + (unsigned)((st * 9 + i) * SEG * (int)sizeof(T)), g, SEG * (unsigned)sizeof(T), full_s + 8u * st);
+            bulk_g2s(stage_s + (unsigned)((st * 9 + i) * SEG * (int)sizeof(T)), g, seg_bytes, full_s + 8u * st);
         }
     };
     if (t == 0) {

@@ -62,3 +62,75 @@ def test_double_step_partition_is_closed_and_exact(boundary, shape):
 
     # the two level-(n+2) regions tile the block
     assert ((d < 2) | (d >= 2)).all()
+
+
+# ---- the fused tile's ring (csrc/temporal.cuh: t2_tile) ---------------------------------------------------------
+# A model of the DATA MOVEMENT of one fused tile with the kernel's own index expressions (ring_slots / ring_base /
+# mirror_k / LBM_SLOT / lag registers), on tagged values instead of numbers: level-(n+1) value (i, row, col) must
+# arrive in the level-(n+2) pull of cell (row + cx_i, col + cy_i).  The ring is sized for ONE barrier per row: a
+# warp that is already past the barrier writes the next row while slower warps still read, so the model performs
+# the writes of iteration s+1 BEFORE the reads of iteration s (the worst interleaving the barrier allows).  rev=True
+# is the mirrored (top-down) walk with E/W roles swapped: measured on the GPU, bit-identical, not faster, not
+# shipped (profiles/r02_t2_order_sweep.log) -- kept here because it pins the ring sizing argument from both sides.
+CX = [0, 1, 0, -1, 0, 1, -1, -1, 1]
+CY = [0, 0, 1, 0, -1, 1, 1, -1, -1]
+Q0, QE, QN, QW, QS, QNE, QNW, QSW, QSE = range(9)
+
+
+def _ring_slots(i):
+    return 2 if i in (QNW, QSW) else 3 if i in (QN, QS) else 4
+
+
+def _ring_base(i):
+    order = [QNW, QSW, QN, QS, QNE, QSE]
+    return sum(_ring_slots(j) for j in order[:order.index(i)])
+
+
+def _mirror_k(i):
+    return {QE: QW, QW: QE, QNE: QNW, QNW: QNE, QSW: QSE, QSE: QSW}.get(i, i)
+
+
+@pytest.mark.parametrize("rev", [False, True])
+@pytest.mark.parametrize("rows", [1, 2, 5, 16])
+def test_fused_tile_ring_walk(rev, rows):
+    width = 12                                   # threads of the model tile
+    k0, k1 = 2, 2 + rows                         # emits rows k0 .. k1-1 from level-(n+1) rows k0-1 .. k1
+    nit = k1 - k0 + 2
+    direction = -1 if rev else 1
+    jfirst = k1 if rev else k0 - 1
+    qlag, qlead = (QW, QE) if rev else (QE, QW)
+    rs = lambda i: _ring_slots(_mirror_k(i) if rev else i)
+    rb = lambda i: _ring_base(_mirror_k(i) if rev else i)
+    ring = {}
+    shifted = (QN, QS, QNE, QNW, QSW, QSE)
+
+    def slot(i, s, d):
+        n = rs(i)
+        return (s - d) % n                       # (s - d) & 1, (s3 + 3 - d) % 3 with s3 = s % 3, (s - d) & 3
+
+    def write(s):
+        row = jfirst + direction * s
+        for t in range(width):
+            for i in shifted:
+                ring[(rb(i) + slot(i, s, 0), t)] = (i, row, t)
+
+    emitted = {}
+    regs = {t: {"rest_m1": None, "lag_m1": None, "lag_m2": None} for t in range(width)}
+    write(0)
+    for s in range(nit):
+        row = jfirst + direction * s
+        if s + 1 < nit:
+            write(s + 1)                         # a fast warp is already one row ahead
+        for t in range(width):
+            r = regs[t]
+            if s >= 2 and 1 <= t < width - 1:
+                g = {Q0: r["rest_m1"], qlag: r["lag_m2"], qlead: (qlead, row, t)}
+                for i in shifted:
+                    g[i] = ring[(rb(i) + slot(i, s, 1 + direction * CX[i]), t - CY[i])]
+                emitted[(row - direction, t)] = g
+            r["lag_m2"], r["lag_m1"], r["rest_m1"] = r["lag_m1"], (qlag, row, t), (Q0, row, t)
+    assert len({rb(i) + n for i in shifted for n in range(rs(i))}) == 18      # the six populations tile the 18 ring rows
+    assert sorted({k for k, _ in emitted}) == list(range(k0, k1))
+    for (row, t), g in emitted.items():
+        for i in range(9):
+            assert g[i] == (i, row - CX[i], t - CY[i]), (rev, row, t, i, g[i])

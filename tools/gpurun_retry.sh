@@ -1,0 +1,11 @@
+#!/bin/bash
+# developer helper: retry a gpurun call while the pod answers "busy" (exit code 3, nothing charged)
+# usage: tools/gpurun_retry.sh <timeout_s> '<command>' [--gpus N]
+T=$1; CMD=$2; shift 2
+for i in $(seq 1 40); do
+  /usr/local/graft/bin/gpurun "$@" --timeout "$T" -- "$CMD"
+  rc=$?
+  if [ $rc -ne 3 ]; then exit $rc; fi
+  sleep 120
+done
+exit 3

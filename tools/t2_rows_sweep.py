@@ -8,9 +8,11 @@ import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import latticeboltzmann_b200 as lb
 
-for n in (2048, 3072, 4096, 8192, 16384):
+SIZES = [int(a) for a in sys.argv[1].split(",")] if len(sys.argv) > 1 else [2048, 3072, 4096, 8192, 16384]
+ROWS = [int(a) for a in sys.argv[2].split(",")] if len(sys.argv) > 2 else [8, 16, 32, 64]
+for n in SIZES:
     res = {"n": n}
-    for rows in (8, 16, 32, 64):
+    for rows in ROWS:
         os.environ["LBM_T2_ROWS"] = str(rows)
         lat = lb.Lattice(n, n, "cavity", omega=2000.0 / (0.6 * n + 1000.0), temporal=2)
         lat.init_equilibrium()
