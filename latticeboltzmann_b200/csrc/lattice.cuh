@@ -51,6 +51,8 @@ struct DevState {
     unsigned int frame_done;               // temporal blocking: frame-kernel CTAs finished in the running launch
     unsigned long long fflag_in[NUM_DIRS]; // temporal blocking: level-(n+1) frame ghosts pushed by the neighbour in slot d
     unsigned long long grid_bar;           // resident multi-step kernel: arrivals at its grid barrier (monotone)
+    unsigned int t2_done;                  // temporal blocking: fused-interior CTAs finished in the running launch
+    unsigned int pass_done;                // temporal blocking: parts of the running pass (interior, frame level n+2) that are complete
 };
 static_assert(sizeof(DevState) <= 256, "the allocation reserves 256 bytes for DevState");
 

@@ -46,6 +46,10 @@ struct lb_lattice {
     bool use_graph = true;
     int temporal = 0;            // 0: auto (two steps per HBM pass when the block is big enough to fill the GPU), 1: single-step kernel, 2: force temporal blocking
     int t2_rows = 0;             // rows per fused tile; 0: automatic (t2_rows_for)
+    // temporal blocking: the frame kernels (K1, K3) run on s_frame concurrently with the fused interior kernel (K2) on `stream`
+    cudaStream_t s_frame = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_int = nullptr, ev_frm = nullptr;
+    bool overlap_frames = true;
     cudaGraphExec_t graph2_exec = nullptr;   // GRAPH_DOUBLE double steps
     cudaStream_t graph2_stream = nullptr;
     int graph2_rows = 0;
@@ -239,7 +243,7 @@ int launch_step(lb_lattice *L, bool collide)
 
 // One double step (temporal.cuh): frame level n+1, fused deep interior, frame level n+2.
 template <typename T, int BC, bool EXACT>
-int launch_double_bc(lb_lattice *L, const StepParams<T> &p, int phases = 7)
+int launch_double_bc(lb_lattice *L, const StepParams<T> &p, int phases, cudaStream_t fs)
 {
     // The fused tile's shared memory exceeds the 48 KB default.  Per device and per instantiation; the call is
     // idempotent, so two host threads racing on the bit mask at worst both make it.
@@ -247,31 +251,82 @@ int launch_double_bc(lb_lattice *L, const StepParams<T> &p, int phases = 7)
     const unsigned long long dev_bit = 1ull << (L->cfg.device & 63);
     if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
         LBM_CUDA(cudaFuncSetAttribute(t2_interior_kernel<T, BC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2_smem_bytes<T>()));
+        // The frame kernels share the SMs with the fused tiles (launch_passes): they ask for the same shared-memory
+        // carve-out, otherwise an SM has to drain its fused tiles before it can take a frame CTA and again afterwards.
+        if (!getenv("LBM_T2_FRAME_CARVEOUT") || atoi(getenv("LBM_T2_FRAME_CARVEOUT"))) {
+            LBM_CUDA(cudaFuncSetAttribute(t2_frame1_kernel<T, BC, EXACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            LBM_CUDA(cudaFuncSetAttribute(t2_frame2_kernel<T, BC, EXACT>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        }
         attr_done.fetch_or(dev_bit, std::memory_order_release);
     }
     const int g1 = (int)((ring_cells(p.lnx, p.lny, FRAME_W) + TILE_L - 1) / TILE_L);
     const int g3 = (int)((ring_cells(p.lnx, p.lny, 2) + TILE_L - 1) / TILE_L);
-    if (phases & 1) t2_frame1_kernel<T, BC, EXACT><<<g1, TILE_L, 0, L->stream>>>(p);
+    if (phases & 1) t2_frame1_kernel<T, BC, EXACT><<<g1, TILE_L, 0, fs>>>(p);
     if (phases & 2) t2_interior_kernel<T, BC, EXACT><<<p.t2_tiles_l * p.t2_tiles_k, T2_TILE, t2_smem_bytes<T>(), L->stream>>>(p);
-    if (phases & 4) t2_frame2_kernel<T, BC, EXACT><<<g3, TILE_L, 0, L->stream>>>(p);
+    if (phases & 4) t2_frame2_kernel<T, BC, EXACT><<<g3, TILE_L, 0, fs>>>(p);
     return 0;
 }
 
+// phases: bit 0 = K1 (frame level n+1), bit 1 = K2 (fused interior), bit 2 = K3 (frame level n+2); the frame kernels
+// go to `fs` (default: the lattice's stream), K2 always to the lattice's stream.
 template <typename T>
-int launch_double(lb_lattice *L, int phases = 7)
+int launch_double(lb_lattice *L, int phases = 7, cudaStream_t fs = nullptr)
 {
     const StepParams<T> p = make_params<T>(L);
     const bool exact = L->cfg.arith == LB_ARITH_EXACT;
+    if (!fs) fs = L->stream;
     switch (L->cfg.boundary) {
     case LB_PERIODIC:
-        return exact ? launch_double_bc<T, BC_PERIODIC, true>(L, p, phases) : launch_double_bc<T, BC_PERIODIC, false>(L, p, phases);
+        return exact ? launch_double_bc<T, BC_PERIODIC, true>(L, p, phases, fs) : launch_double_bc<T, BC_PERIODIC, false>(L, p, phases, fs);
     case LB_CAVITY:
-        return exact ? launch_double_bc<T, BC_CAVITY, true>(L, p, phases) : launch_double_bc<T, BC_CAVITY, false>(L, p, phases);
+        return exact ? launch_double_bc<T, BC_CAVITY, true>(L, p, phases, fs) : launch_double_bc<T, BC_CAVITY, false>(L, p, phases, fs);
     case LB_CAVITY_XPERIODIC:
-        return exact ? launch_double_bc<T, BC_CAVITY_XPERIODIC, true>(L, p, phases) : launch_double_bc<T, BC_CAVITY_XPERIODIC, false>(L, p, phases);
+        return exact ? launch_double_bc<T, BC_CAVITY_XPERIODIC, true>(L, p, phases, fs) : launch_double_bc<T, BC_CAVITY_XPERIODIC, false>(L, p, phases, fs);
     default:
         return lbm_fail(LB_ERR_INVALID, "temporal blocking supports the periodic and cavity boundaries");
     }
+}
+
+int launch_double_any(lb_lattice *L, int phases = 7, cudaStream_t fs = nullptr)
+{
+    return L->cfg.dtype == LB_F64 ? launch_double<double>(L, phases, fs) : launch_double<float>(L, phases, fs);
+}
+
+// The second stream and the events of the overlapped pass (created outside any stream capture).
+int ensure_frame_stream(lb_lattice *L)
+{
+    if (L->s_frame) return 0;
+    int least = 0, greatest = 0;
+    LBM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    LBM_CUDA(cudaStreamCreateWithPriority(&L->s_frame, cudaStreamNonBlocking, greatest));   // frame CTAs slip in between the interior's
+    LBM_CUDA(cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming));
+    LBM_CUDA(cudaEventCreateWithFlags(&L->ev_int, cudaEventDisableTiming));
+    LBM_CUDA(cudaEventCreateWithFlags(&L->ev_frm, cudaEventDisableTiming));
+    return 0;
+}
+
+// n passes (2n time steps) of one block.  K1 -> K3 of a pass run on s_frame while K2 runs on the lattice's stream;
+// the next pass starts when both are complete: its K2 reads what K3 wrote (cells closer than 2 to the perimeter),
+// its K1 reads what K2 wrote (distance 2 and 3) and overwrites the frame storage K3 read.  On return all work is
+// joined into the lattice's stream.  Capturable (the graph of GRAPH_DOUBLE passes forks and joins inside).
+int launch_passes(lb_lattice *L, int n)
+{
+    if (!L->overlap_frames) {
+        for (int i = 0; i < n; ++i)
+            if (int r = launch_double_any(L)) return r;
+        return 0;
+    }
+    LBM_CUDA(cudaEventRecord(L->ev_fork, L->stream));
+    LBM_CUDA(cudaStreamWaitEvent(L->s_frame, L->ev_fork, 0));
+    for (int i = 0; i < n; ++i) {
+        if (int r = launch_double_any(L, 2)) return r;
+        LBM_CUDA(cudaEventRecord(L->ev_int, L->stream));
+        if (int r = launch_double_any(L, 1 | 4, L->s_frame)) return r;
+        LBM_CUDA(cudaEventRecord(L->ev_frm, L->s_frame));
+        LBM_CUDA(cudaStreamWaitEvent(L->stream, L->ev_frm, 0));
+        LBM_CUDA(cudaStreamWaitEvent(L->s_frame, L->ev_int, 0));
+    }
+    return 0;
 }
 
 constexpr int GRAPH_DOUBLE = 32;     // double steps per graph launch (64 time steps)
@@ -284,8 +339,7 @@ int ensure_graph2(lb_lattice *L)
     // first launch outside the capture: it sets the kernels' shared-memory attribute
     cudaGraph_t g = nullptr;
     LBM_CUDA(cudaStreamBeginCapture(L->stream, cudaStreamCaptureModeThreadLocal));
-    int r = 0;
-    for (int s = 0; s < GRAPH_DOUBLE && !r; ++s) r = L->cfg.dtype == LB_F64 ? launch_double<double>(L) : launch_double<float>(L);
+    const int r = launch_passes(L, GRAPH_DOUBLE);
     cudaError_t e = cudaStreamEndCapture(L->stream, &g);
     if (r || e != cudaSuccess) {
         if (g) cudaGraphDestroy(g);
@@ -613,6 +667,7 @@ int lb_create_ex(const lb_config *cfg, int flags, lb_lattice **out)
     if (const char *t = getenv("LBM_RESIDENT")) L->use_resident = atoi(t) != 0;
     if (const char *t = getenv("LBM_RESIDENT2")) L->use_resident2 = atoi(t) != 0;
     if (const char *t = getenv("LBM_T2_ROWS")) if (atoi(t) > 0) L->t2_rows = atoi(t);
+    if (const char *t = getenv("LBM_T2_OVERLAP")) L->overlap_frames = atoi(t) != 0;
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
     *out = L;
@@ -646,6 +701,10 @@ int lb_destroy(lb_lattice *L)
     if (L->d_cols) cudaFree(L->d_cols);
     if (L->s_h2d) cudaStreamDestroy(L->s_h2d);
     if (L->s_d2h) cudaStreamDestroy(L->s_d2h);
+    if (L->ev_fork) cudaEventDestroy(L->ev_fork);
+    if (L->ev_int) cudaEventDestroy(L->ev_int);
+    if (L->ev_frm) cudaEventDestroy(L->ev_frm);
+    if (L->s_frame) cudaStreamDestroy(L->s_frame);
     if (L->ev0) cudaEventDestroy(L->ev0);
     if (L->ev1) cudaEventDestroy(L->ev1);
     if (L->own_stream) cudaStreamDestroy(L->own_stream);
@@ -687,7 +746,7 @@ int lb_double_step_phase(lb_lattice *L, int phase)
     if (phase < 1 || phase > 3) return lbm_fail(LB_ERR_INVALID, "phase must be 1, 2 or 3");
     if (!temporal_ok(L)) return lbm_fail(LB_ERR_STATE, "temporal blocking is not available for this lattice");
     LBM_ON_DEVICE(L);
-    int r = L->cfg.dtype == LB_F64 ? launch_double<double>(L, 1 << (phase - 1)) : launch_double<float>(L, 1 << (phase - 1));
+    int r = launch_double_any(L, 1 << (phase - 1));
     if (r) return r;
     L->launches++;
     if (phase == 3) {
@@ -1000,9 +1059,11 @@ int lb_step(lb_lattice *L, int64_t nsteps)
     if (L->inplace) return aa_step(L, nsteps);
     // Temporal blocking: two steps per pass over HBM (three launches per double step).
     if (temporal_ok(L)) {
+        if (L->overlap_frames)
+            if (int r = ensure_frame_stream(L)) return r;
         if (L->use_graph && nsteps >= 4 * GRAPH_DOUBLE) {
             // one eager double step first: it sets the fused kernel's shared-memory attribute outside any capture
-            int r = L->cfg.dtype == LB_F64 ? launch_double<double>(L) : launch_double<float>(L);
+            int r = launch_passes(L, 1);
             if (r) return r;
             L->launches += 3;
             L->steps += 2;
@@ -1016,13 +1077,13 @@ int lb_step(lb_lattice *L, int64_t nsteps)
                 nsteps -= 2 * GRAPH_DOUBLE;
             }
         }
-        while (nsteps >= 2) {
-            int r = L->cfg.dtype == LB_F64 ? launch_double<double>(L) : launch_double<float>(L);
-            if (r) return r;
-            L->launches += 3;
-            L->steps += 2;
-            L->cur ^= 1;
-            nsteps -= 2;
+        if (nsteps >= 2) {
+            const int passes = (int)(nsteps / 2);
+            if (int r = launch_passes(L, passes)) return r;
+            L->launches += 3ll * passes;
+            L->steps += 2ll * passes;
+            L->cur ^= passes & 1;
+            nsteps -= 2ll * passes;
         }
         LBM_CUDA(cudaGetLastError());
     }

@@ -22,8 +22,15 @@
 //
 // Flag protocol (monotone counters in DevState, same reasoning as step_kernel.cuh): K1 waits for
 // flag_in >= n (level-n main ghosts present, neighbours done with the frame ghosts K1 overwrites), K3
-// waits for fflag_in >= n+1 (level-(n+1) frame ghosts present).  K2 runs between them on the same
-// stream and gives the exchange a whole interior update of slack.
+// waits for fflag_in >= n+1 (level-(n+1) frame ghosts present).
+//
+// K2 touches neither ghosts nor frame storage nor flags, and K1 / K3 touch no deep-interior cell of the destination
+// buffer, so lb_step runs K1 -> K3 on a second (high-priority) stream CONCURRENTLY with K2 and joins the two at the
+// end of the pass (lattice_api.cu: launch_passes): the small latency-bound frame kernels and the halo exchange hide
+// behind the interior update instead of adding to it.  Whichever of K2 / K3 finishes second publishes the pass
+// (t2_part_done): buffer flip + step counter, which the kernels of the NEXT pass read.  Drivers that interleave
+// several blocks on one stream (lb_double_step_phase) run the three kernels in order; the same rule then makes K3
+// the publisher.
 #pragma once
 #include "step_kernel.cuh"
 
@@ -282,6 +289,18 @@ __device__ __forceinline__ void wait_flags(const unsigned long long *flags, unsi
     __syncthreads();
 }
 
+// One of the two parts of a pass that write the destination buffer (K2, K3) is complete; the second one to get here
+// publishes the pass.  The kernels of the next pass are ordered after BOTH parts by the host (stream order / events).
+__device__ __forceinline__ void t2_part_done(DevState *st, int par)
+{
+    if (atomicAdd(&st->pass_done, 1u) == 1u) {
+        st->pass_done = 0u;
+        const unsigned long long step = *(volatile unsigned long long *)&st->step;
+        *(volatile unsigned int *)&st->cur = (unsigned int)(par ^ 1);   // ONE buffer flip per pass, two steps
+        *(volatile unsigned long long *)&st->step = step + 2ull;
+    }
+}
+
 // K1: level n -> n+1 on the frame.
 template <typename T, int BC, bool EXACT>
 __global__ void __launch_bounds__(TILE_L) t2_frame1_kernel(const __grid_constant__ StepParams<T> p)
@@ -349,8 +368,7 @@ __global__ void __launch_bounds__(TILE_L) t2_frame2_kernel(const __grid_constant
             halo_fence(p.sys_scope);
 #pragma unroll
             for (int d = 0; d < NUM_DIRS; ++d) st_relaxed_sys(p.nbr[d].flag_in + dir_opp(d), step + 2ull);
-            *(volatile unsigned int *)&st->cur = (unsigned int)(par ^ 1);  // ONE buffer flip per pass, two steps
-            *(volatile unsigned long long *)&st->step = step + 2ull;     // K1 and K2 of this double step are complete (stream order)
+            t2_part_done(st, par);
         }
     }
 }
@@ -506,6 +524,15 @@ __global__ void __launch_bounds__(T2_TILE, t2_minb<T>()) t2_interior_kernel(cons
         e_m1 = e_0;
         rest_m1 = rest_0;
         s3 = s3 == 2 ? 0 : s3 + 1;
+    }
+    // the last tile to finish marks the interior part of the pass complete (this CTA read `par` before any flip:
+    // the pass is published only after every interior CTA has been counted)
+    if (t == 0) {
+        const unsigned int prev = atomicAdd(&p.st->t2_done, 1u);
+        if (prev == gridDim.x - 1u) {
+            p.st->t2_done = 0u;
+            t2_part_done(p.st, par);
+        }
     }
 }
 
