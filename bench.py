@@ -250,10 +250,10 @@ def timed_lattice(D, nx, ny, ndx, ndy, omega, dtype, arith, device, temporal, wa
     return lat, ms, lat.checksum()
 
 
-def strip_rows(lnx, rows=64):
-    """A strip of `rows` rows in the middle of the block that straddles two row seams of the fused tiles
-    (tiles start at row 2 + 32 m)."""
-    a = 2 + 32 * max(1, lnx // 64) - 16
+def strip_rows(lnx, tile_rows, rows=64):
+    """A strip of `rows` rows in the middle of the block centred on a row seam of the fused tiles (tiles start at
+    row 2 + tile_rows * m; with tiles of at most 32 rows the strip straddles two seams)."""
+    a = 2 + tile_rows * max(1, (lnx // 2) // tile_rows) - rows // 2
     return (a, a + rows) if a - 2 >= 0 and a + rows + 2 <= lnx else None
 
 
@@ -365,7 +365,7 @@ def main():
     # two-row halo, one more pass of the stepping kernel, level n+2 rows.
     strip = None
     if rank == 0 and args.gpus == 1 and not args.no_cpu_baseline and not args.no_extras:
-        rows = strip_rows(b.lnx)
+        rows = strip_rows(b.lnx, lat.block.temporal_rows)
         if rows:
             pre = lat.block.download_rows(rows[0] - 2, rows[1] + 2)
             lat.step(2)

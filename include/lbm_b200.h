@@ -214,7 +214,8 @@ LB_API int lb_set_halo_timeout_ms(lb_lattice *lat, int64_t ms);
  * 0 (default) = automatic: temporal blocking when the block offers at least 512 fused tiles of 16 rows (about
  * 1400^2 cells), else the single-step kernel.  The mode is a COLLECTIVE property of a decomposition: blocks that
  * exchange halos must all use the same mode (latticeboltzmann_b200.distributed decides it for the whole
- * world and sets 1 or 2 explicitly).  rows_per_tile > 0 overrides the fused tile height (default 16 or 32 by block size).
+ * world and sets 1 or 2 explicitly).  rows_per_tile > 0 overrides the fused tile height (default 16 .. 96 by block size;
+ * lb_temporal_rows returns the height in use).
  * Environment override: LBM_TEMPORAL=0|1|2.                                                        */
 LB_API int lb_set_temporal(lb_lattice *lat, int steps_per_pass, int rows_per_tile);
 /* One phase (1, 2, 3) of a temporal-blocking double step, for drivers that run several blocks on ONE
@@ -222,6 +223,7 @@ LB_API int lb_set_temporal(lb_lattice *lat, int steps_per_pass, int rows_per_til
  * interleaved.  lb_temporal_active tells whether lb_step uses double steps for this lattice.       */
 LB_API int lb_double_step_phase(lb_lattice *lat, int phase);
 LB_API int lb_temporal_active(lb_lattice *lat);
+LB_API int lb_temporal_rows(lb_lattice *lat);
 /* lb_step replays a CUDA graph of 64 fused steps for long runs (default on).                */
 LB_API int lb_set_use_graph(lb_lattice *lat, int on);
 /* L2-resident lattices (a single self-connected block of at most 2^20 cells that does not use temporal

@@ -83,6 +83,7 @@ SYMBOLS = {
     "lb_set_temporal": (ctypes.c_int, [c_vp, ctypes.c_int, ctypes.c_int]),
     "lb_double_step_phase": (ctypes.c_int, [c_vp, ctypes.c_int]),
     "lb_temporal_active": (ctypes.c_int, [c_vp]),
+    "lb_temporal_rows": (ctypes.c_int, [c_vp]),
     "lb_pitch": (c_i64, [c_vp]),
     "lb_pop_stride": (c_i64, [c_vp]),
     "lb_kernel_launches": (ctypes.c_int, [c_vp, _P(c_i64)]),

@@ -50,6 +50,7 @@ struct lb_lattice {
     cudaStream_t s_frame = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_int = nullptr, ev_frm = nullptr;
     bool overlap_frames = true;
+    bool t2_pipe = false;        // software-pipelined fused kernel (temporal.cuh: t2_interior_pipe_kernel)
     cudaGraphExec_t graph2_exec = nullptr;   // GRAPH_DOUBLE double steps
     cudaStream_t graph2_stream = nullptr;
     int graph2_rows = 0;
@@ -120,16 +121,21 @@ void drop_graph(lb_lattice *L)
 
 DevState *dev_state(lb_lattice *L) { return reinterpret_cast<DevState *>(L->base + L->state_off); }
 
-// Rows per fused tile.  64-row tiles recompute half as many level-(n+1) halo rows (2 per 64) but measured no
-// faster with the TMA-staged fp64 kernel (16384^2 EXACT: 87.1 vs 87.5 GLUPS), so 32 is its default; fp32 gains 2 % (147.0 vs 143.9).
-// Smaller lattices take 16-row tiles so that enough tiles remain to fill 148 SMs x 2 CTAs (profiles/r02_t2_rows_sweep.log,
-// r02_t2_small_sweep.log: 1536^2 45.4 (16 rows) vs 39.5 (32 rows) GLUPS; 4096^2 77.0 (32) vs 74.2 (16)).
+// Rows per fused tile.  Taller tiles recompute (and re-read) fewer level-(n+1) halo rows -- 2 per tile -- but leave
+// fewer tiles to balance over 148 SMs x 2 CTAs.  Interleaved A/B in one process (tools/t2_env_ab.py,
+// profiles/r02_t2_rows_ab.log; sustained clocks under the power cap, fp64 EXACT GLUPS): 16384^2: 24 rows 80.2, 32 rows
+// 80.1-81.8, 48 rows 83.0, 64 rows 82.0-83.5, 96 rows 83.0, 128 rows 82.6; 8192^2: 32 rows 78.8, 48 rows 79.3, 64 rows
+// 79.1, 96 rows 79.0; 4096^2: 24 .. 48 rows within 1 % (64 rows: -4 %, too few tiles).  fp32 gains 2 % from 64 rows
+// (147.0 vs 143.9).  Smaller lattices take 16-row tiles so that enough tiles remain (profiles/r02_t2_rows_sweep.log,
+// r02_t2_small_sweep.log: 1536^2 45.4 (16 rows) vs 39.5 (32 rows) GLUPS).
 int t2_rows_for(const lb_lattice *L)
 {
     if (L->t2_rows > 0) return L->t2_rows;
     const long long tl = t2_tiles_over(L->cfg.lny);
     auto tiles = [&](int rows) { return tl * ((L->cfg.lnx - 4 + rows - 1) / rows); };
     if (L->cfg.dtype == LB_F32 && tiles(64) >= 1024) return 64;
+    if (tiles(96) >= 8192) return 96;
+    if (tiles(64) >= 4096) return 64;
     return tiles(32) >= 1024 ? 32 : 16;
 }
 
@@ -251,6 +257,9 @@ int launch_double_bc(lb_lattice *L, const StepParams<T> &p, int phases, cudaStre
     const unsigned long long dev_bit = 1ull << (L->cfg.device & 63);
     if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
         LBM_CUDA(cudaFuncSetAttribute(t2_interior_kernel<T, BC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2_smem_bytes<T>()));
+#if LBM_T2_TMA
+        LBM_CUDA(cudaFuncSetAttribute(t2_interior_pipe_kernel<T, BC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2_smem_bytes<T>()));
+#endif
         // The frame kernels share the SMs with the fused tiles (launch_passes): they ask for the same shared-memory
         // carve-out, otherwise an SM has to drain its fused tiles before it can take a frame CTA and again afterwards.
         if (!getenv("LBM_T2_FRAME_CARVEOUT") || atoi(getenv("LBM_T2_FRAME_CARVEOUT"))) {
@@ -262,6 +271,10 @@ int launch_double_bc(lb_lattice *L, const StepParams<T> &p, int phases, cudaStre
     const int g1 = (int)((ring_cells(p.lnx, p.lny, FRAME_W) + TILE_L - 1) / TILE_L);
     const int g3 = (int)((ring_cells(p.lnx, p.lny, 2) + TILE_L - 1) / TILE_L);
     if (phases & 1) t2_frame1_kernel<T, BC, EXACT><<<g1, TILE_L, 0, fs>>>(p);
+#if LBM_T2_TMA
+    if ((phases & 2) && L->t2_pipe) t2_interior_pipe_kernel<T, BC, EXACT><<<p.t2_tiles_l * p.t2_tiles_k, T2_TILE, t2_smem_bytes<T>(), L->stream>>>(p);
+    else
+#endif
     if (phases & 2) t2_interior_kernel<T, BC, EXACT><<<p.t2_tiles_l * p.t2_tiles_k, T2_TILE, t2_smem_bytes<T>(), L->stream>>>(p);
     if (phases & 4) t2_frame2_kernel<T, BC, EXACT><<<g3, TILE_L, 0, fs>>>(p);
     return 0;
@@ -668,6 +681,7 @@ int lb_create_ex(const lb_config *cfg, int flags, lb_lattice **out)
     if (const char *t = getenv("LBM_RESIDENT2")) L->use_resident2 = atoi(t) != 0;
     if (const char *t = getenv("LBM_T2_ROWS")) if (atoi(t) > 0) L->t2_rows = atoi(t);
     if (const char *t = getenv("LBM_T2_OVERLAP")) L->overlap_frames = atoi(t) != 0;
+    if (const char *t = getenv("LBM_T2_PIPE")) L->t2_pipe = atoi(t) != 0;
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
     *out = L;
@@ -756,6 +770,9 @@ int lb_double_step_phase(lb_lattice *L, int phase)
     LBM_CUDA(cudaGetLastError());
     return 0;
 }
+
+/* Rows per fused tile that lb_step would use for this lattice in two-steps-per-pass mode. */
+int lb_temporal_rows(lb_lattice *L) { return L ? t2_rows_for(L) : 0; }
 
 /* 1 if lb_step advances this lattice two steps per pass (temporal blocking), else 0. */
 int lb_temporal_active(lb_lattice *L) { return L && temporal_ok(L) ? 1 : 0; }

@@ -80,6 +80,11 @@ class Block:
     def temporal_active(self):
         return bool(self.lib.lb_temporal_active(self.h))
 
+    @property
+    def temporal_rows(self):
+        """Rows per fused tile of the two-steps-per-pass kernel (tiles start at row 2 + m * temporal_rows)."""
+        return int(self.lib.lb_temporal_rows(self.h))
+
     def set_boundary_table(self, cells, src, add):
         """Per-cell boundary table of an "sf_table" lattice (boundary_table.py: cells (n,), src (n, 9), add (n, 9))."""
         cells = np.ascontiguousarray(cells, dtype=np.int64)
