@@ -50,7 +50,6 @@ struct lb_lattice {
     cudaStream_t s_frame = nullptr;
     cudaEvent_t ev_fork = nullptr, ev_int = nullptr, ev_frm = nullptr;
     bool overlap_frames = true;
-    bool t2_pipe = false;        // software-pipelined fused kernel (temporal.cuh: t2_interior_pipe_kernel)
     cudaGraphExec_t graph2_exec = nullptr;   // GRAPH_DOUBLE double steps
     cudaStream_t graph2_stream = nullptr;
     int graph2_rows = 0;
@@ -257,9 +256,6 @@ int launch_double_bc(lb_lattice *L, const StepParams<T> &p, int phases, cudaStre
     const unsigned long long dev_bit = 1ull << (L->cfg.device & 63);
     if (!(attr_done.load(std::memory_order_acquire) & dev_bit)) {
         LBM_CUDA(cudaFuncSetAttribute(t2_interior_kernel<T, BC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2_smem_bytes<T>()));
-#if LBM_T2_TMA
-        LBM_CUDA(cudaFuncSetAttribute(t2_interior_pipe_kernel<T, BC, EXACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, t2_smem_bytes<T>()));
-#endif
         // The frame kernels share the SMs with the fused tiles (launch_passes): they ask for the same shared-memory
         // carve-out, otherwise an SM has to drain its fused tiles before it can take a frame CTA and again afterwards.
         if (!getenv("LBM_T2_FRAME_CARVEOUT") || atoi(getenv("LBM_T2_FRAME_CARVEOUT"))) {
@@ -271,10 +267,6 @@ int launch_double_bc(lb_lattice *L, const StepParams<T> &p, int phases, cudaStre
     const int g1 = (int)((ring_cells(p.lnx, p.lny, FRAME_W) + TILE_L - 1) / TILE_L);
     const int g3 = (int)((ring_cells(p.lnx, p.lny, 2) + TILE_L - 1) / TILE_L);
     if (phases & 1) t2_frame1_kernel<T, BC, EXACT><<<g1, TILE_L, 0, fs>>>(p);
-#if LBM_T2_TMA
-    if ((phases & 2) && L->t2_pipe) t2_interior_pipe_kernel<T, BC, EXACT><<<p.t2_tiles_l * p.t2_tiles_k, T2_TILE, t2_smem_bytes<T>(), L->stream>>>(p);
-    else
-#endif
     if (phases & 2) t2_interior_kernel<T, BC, EXACT><<<p.t2_tiles_l * p.t2_tiles_k, T2_TILE, t2_smem_bytes<T>(), L->stream>>>(p);
     if (phases & 4) t2_frame2_kernel<T, BC, EXACT><<<g3, TILE_L, 0, fs>>>(p);
     return 0;
@@ -681,7 +673,6 @@ int lb_create_ex(const lb_config *cfg, int flags, lb_lattice **out)
     if (const char *t = getenv("LBM_RESIDENT2")) L->use_resident2 = atoi(t) != 0;
     if (const char *t = getenv("LBM_T2_ROWS")) if (atoi(t) > 0) L->t2_rows = atoi(t);
     if (const char *t = getenv("LBM_T2_OVERLAP")) L->overlap_frames = atoi(t) != 0;
-    if (const char *t = getenv("LBM_T2_PIPE")) L->t2_pipe = atoi(t) != 0;
     const char *env = getenv("LBM_ROWS_PER_TILE");
     if (env && atoi(env) > 0) L->rows_per_tile = atoi(env);
     *out = L;

@@ -71,6 +71,10 @@ __host__ __device__ inline int t2_tiles_over(long long lny) { return lny > 4 ? (
 // plain band-major upward walk at 16384^2 (4096^2: 76.3 ... 69.6 vs 75.9) -- no gain (the kernel is not limited by
 // the 3.5 % of redundant reads alone), column-major order is 13 % slower; removed again.  Tile heights 24 .. 48 are
 // within 1 % of each other at 3072^2 .. 8192^2 (profiles/r02_t2_rows_sweep.log).
+// Software pipelining (profiles/r02_t2_pipe_ab.log): the level-(n+2) update of row j-1 and the level-(n+1) update of
+// row j+1 issued as ONE straight-line block between the same two barriers (two independent collision chains per
+// warp against the `wait` stalls ncu reports, 102 registers): 82.3 vs 83.2 GLUPS at 16384^2, 73.1 vs 74.9 at 4096^2 in
+// an interleaved A/B, bit-identical -- slower, removed again.
 #ifndef LBM_T2_COMPACT_RING
 #define LBM_T2_COMPACT_RING 1
 #endif
@@ -535,178 +539,5 @@ __global__ void __launch_bounds__(T2_TILE, t2_minb<T>()) t2_interior_kernel(cons
         }
     }
 }
-
-#if LBM_T2_TMA
-// K2, software-pipelined: the level-(n+2) update of row j-1 and the level-(n+1) update of row j+1 -- both legal
-// between the same two row barriers -- are issued as ONE straight-line block, so each warp carries two independent
-// collision chains instead of one (the plain loop stalls on fixed-latency dependencies: 2.0 of 7.6 warp cycles per
-// issued instruction at 4 warps per scheduler, profiles/r02_t2_interior_16384_details.txt).  Same ring, same barriers,
-// same per-cell arithmetic; threads without a cell of their own work on a neighbour's column (real data, results
-// dropped) so that the block has no divergent branches.
-template <typename T, int BC, bool EXACT>
-__global__ void __launch_bounds__(T2_TILE, t2_minb<T>()) t2_interior_pipe_kernel(const __grid_constant__ StepParams<T> p)
-{
-    extern __shared__ __align__(128) unsigned char t2_smem_raw[];
-    T *ring = reinterpret_cast<T *>(t2_smem_raw);               // [T2_RING_ROWS][T2_TILE]
-    const int par = (int)*(volatile unsigned int *)&p.st->cur;
-    const T *__restrict__ src = p.buf[par];
-    T *__restrict__ dst = p.buf[par ^ 1];
-
-    const int kt = (int)blockIdx.x / p.t2_tiles_l, lt = (int)blockIdx.x - kt * p.t2_tiles_l;
-    const int k0 = 2 + kt * p.t2_rows;
-    const int k1 = min(k0 + p.t2_rows, p.lnx - 2);
-    const int nit = k1 - k0 + 2;                                // level-(n+1) rows k0-1 .. k1 = iterations 0 .. nit-1
-    const int t = threadIdx.x;
-    const int lc = lt * T2_W + T2_S - T2_OFF + t;               // this thread's column (level n+1 and level n+2)
-    const bool have1 = t >= T2_OFF - 1 && t <= T2_OFF + T2_W && lc >= 1 && lc <= p.lny - 2;   // a level-(n+1) cell at distance >= 1
-    const bool have2 = t >= T2_OFF && t < T2_OFF + T2_W && lc >= 2 && lc <= p.lny - 3;        // a level-(n+2) cell at distance >= 2
-    const int ta = have1 ? t : 0;                               // column whose level-(n+1) cell this thread computes (thread 0's is always real)
-    const int tb = have2 ? t : T2_OFF;                          // ... and level-(n+2) cell (the tile's first output column is always real)
-    T *dp = dst + (long long)(k0 + 1) * p.pitch + (lc + PAD_L);                                           // row k0
-    constexpr int AL = 16 / (int)sizeof(T), SEG = t2_seg_elems<T>(), NST = t2_stages<T>();
-    const T *stage = ring + T2_RING_ROWS * T2_TILE;             // [NST][9][SEG]
-    const unsigned stage_s = smem_u32(stage);
-    const unsigned full_s = stage_s + NST * 9 * SEG * (unsigned)sizeof(T);   // NST mbarriers, 8 bytes each
-    const int lc0 = lt * T2_W + T2_S - T2_OFF;                  // column of thread 0
-    const int ncols = min(T2_TILE, p.lny - 1 - lc0);            // see t2_interior_kernel
-    const unsigned seg_bytes = (unsigned)(((ncols + AL - 1 + AL - 1) / AL) * AL * (int)sizeof(T));
-    auto stage_row = [&](int it, int st) {                      // stage `st` <- the nine source segments of iteration `it`
-        const int row = k0 - 1 + it;
-        mbar_expect_tx(full_s + 8u * st, 9u * seg_bytes);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) {
-            const T *g = src + (long long)i * p.pop_stride + (long long)(row - cx_of(i) + 1) * p.pitch + (PAD_L + (((lc0 - cy_of(i)) / AL) * AL));
-            bulk_g2s(stage_s + (unsigned)((st * 9 + i) * SEG * (int)sizeof(T)), g, seg_bytes, full_s + 8u * st);
-        }
-    };
-    if (t == 0) {
-#pragma unroll
-        for (int st = 0; st < NST; ++st) mbar_init(full_s + 8u * st, 1u);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        fence_proxy_async();
-#pragma unroll
-        for (int st = 0; st < NST; ++st)
-            if (st < nit) stage_row(st, st);
-    }
-    __syncthreads();
-
-    int st_cur = 0;                                             // stage (and its parity) of the next iteration to load
-    unsigned st_par = 0u;
-    int st_free = 0;                                            // stage of the iteration loaded last: free after the next barrier
-    // level n+1 in registers, this thread's column: rest / E / W of iteration s (r0, e0, w0), rest / E of s-1, E of s-2
-    T r0 = T(0), e0 = T(0), w0 = T(0), r1 = T(0), e1 = T(0), e2 = T(0);
-    int w3 = 0;                                                 // (iteration being written) % 3
-
-    auto load_a = [&](T (&f)[9]) {                              // the nine level-n sources of the next iteration
-        mbar_wait(full_s + 8u * st_cur, st_par);
-#pragma unroll
-        for (int i = 0; i < 9; ++i) f[i] = stage[(st_cur * 9 + i) * SEG + ((lc0 - cy_of(i)) & (AL - 1)) + ta];
-        if (++st_cur == NST) { st_cur = 0; st_par ^= 1u; }
-    };
-    auto put_a = [&](int w, const T (&f)[9]) {                  // level n+1 of iteration w: ring + registers
-        if (have1) {
-#define LBM_RING_W(I) ring[(ring_base(I) + (ring_slots(I) == 2 ? (w & 1) : ring_slots(I) == 3 ? w3 : (w & 3))) * T2_TILE + t] = f[I]
-            LBM_RING_W(QN);
-            LBM_RING_W(QS);
-            LBM_RING_W(QNE);
-            LBM_RING_W(QNW);
-            LBM_RING_W(QSW);
-            LBM_RING_W(QSE);
-#undef LBM_RING_W
-        }
-        e2 = e1;
-        e1 = e0;
-        r1 = r0;
-        r0 = f[Q0];
-        e0 = f[QE];
-        w0 = f[QW];
-        w3 = w3 == 2 ? 0 : w3 + 1;
-    };
-    // after the barrier that closes iteration s: the stage iteration s was loaded from is free
-    auto refill = [&](int s) {
-        if (t == 0 && s + NST < nit) {
-            fence_proxy_async();
-            stage_row(s + NST, st_free);
-        }
-        if (++st_free == NST) st_free = 0;
-    };
-    // level-(n+2) pull of the row of iteration s-1 (rows of iterations s-2, s-1, s are in the ring / registers);
-    // s3 = s % 3.  Must run before put_a(s + 1) shifts the registers.
-    auto gather_b = [&](int s, int s3, T (&g)[9]) {
-        g[Q0] = r1;
-        g[QE] = e2;
-        g[QW] = w0;
-#define LBM_SLOT(I, D) (ring_slots(I) == 2 ? ((s - (D)) & 1) : ring_slots(I) == 3 ? ((s3 + 3 - (D)) % 3) : ((s - (D)) & 3))
-#define LBM_RING(I) ring[(ring_base(I) + LBM_SLOT(I, 1 + cx_of(I))) * T2_TILE + (tb - cy_of(I))]
-        g[QN] = LBM_RING(QN);
-        g[QS] = LBM_RING(QS);
-        g[QNE] = LBM_RING(QNE);
-        g[QNW] = LBM_RING(QNW);
-        g[QSW] = LBM_RING(QSW);
-        g[QSE] = LBM_RING(QSE);
-#undef LBM_RING
-#undef LBM_SLOT
-    };
-    auto store_b = [&](const T (&g)[9]) {
-        if (have2) {
-            T *q = dp;
-#pragma unroll
-            for (int i = 0; i < 9; ++i) {
-                *q = g[i];
-                q += p.pop_stride;
-            }
-        }
-        dp += p.pitch;
-    };
-
-    // iterations 0, 1, 2 of level n+1 (nit >= 3): nothing to emit yet
-    {
-        T f[9];
-        load_a(f);
-        d2q9_collide<T, EXACT>(f, p.omega);
-        put_a(0, f);
-    }
-#pragma unroll 1
-    for (int s = 0; s < 2; ++s) {
-        __syncthreads();
-        refill(s);
-        T f[9];
-        load_a(f);
-        d2q9_collide<T, EXACT>(f, p.omega);
-        put_a(s + 1, f);
-    }
-    // steady state, between the barriers that close iterations s and s+1: emit the row of iteration s-1 AND produce
-    // level n+1 of iteration s+1
-    int s3 = 2;
-#pragma unroll 1
-    for (int s = 2; s < nit - 1; ++s) {
-        __syncthreads();
-        refill(s);
-        T g[9], f[9];
-        gather_b(s, s3, g);
-        load_a(f);
-        d2q9_collide<T, EXACT>(g, p.omega);
-        d2q9_collide<T, EXACT>(f, p.omega);
-        store_b(g);
-        put_a(s + 1, f);
-        s3 = s3 == 2 ? 0 : s3 + 1;
-    }
-    // the last row
-    {
-        __syncthreads();
-        T g[9];
-        gather_b(nit - 1, s3, g);
-        d2q9_collide<T, EXACT>(g, p.omega);
-        store_b(g);
-    }
-    if (t == 0) {
-        const unsigned int prev = atomicAdd(&p.st->t2_done, 1u);
-        if (prev == gridDim.x - 1u) {
-            p.st->t2_done = 0u;
-            t2_part_done(p.st, par);
-        }
-    }
-}
-#endif
 
 }  // namespace lbm
