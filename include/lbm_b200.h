@@ -214,7 +214,7 @@ LB_API int lb_set_halo_timeout_ms(lb_lattice *lat, int64_t ms);
  * 0 (default) = automatic: temporal blocking when the block offers at least 512 fused tiles of 16 rows (about
  * 1400^2 cells), else the single-step kernel.  The mode is a COLLECTIVE property of a decomposition: blocks that
  * exchange halos must all use the same mode (latticeboltzmann_b200.distributed decides it for the whole
- * world and sets 1 or 2 explicitly).  rows_per_tile > 0 overrides the fused tile height (default 16 .. 96 by block size;
+ * world and sets 1 or 2 explicitly).  rows_per_tile > 0 overrides the fused tile height (default 16, 32 or 48 by block size;
  * lb_temporal_rows returns the height in use).
  * Environment override: LBM_TEMPORAL=0|1|2.                                                        */
 LB_API int lb_set_temporal(lb_lattice *lat, int steps_per_pass, int rows_per_tile);

@@ -121,20 +121,22 @@ void drop_graph(lb_lattice *L)
 DevState *dev_state(lb_lattice *L) { return reinterpret_cast<DevState *>(L->base + L->state_off); }
 
 // Rows per fused tile.  Taller tiles recompute (and re-read) fewer level-(n+1) halo rows -- 2 per tile -- but leave
-// fewer tiles to balance over 148 SMs x 2 CTAs.  Interleaved A/B in one process (tools/t2_env_ab.py,
-// profiles/r02_t2_rows_ab.log; sustained clocks under the power cap, fp64 EXACT GLUPS): 16384^2: 24 rows 80.2, 32 rows
-// 80.1-81.8, 48 rows 83.0, 64 rows 82.0-83.5, 96 rows 83.0, 128 rows 82.6; 8192^2: 32 rows 78.8, 48 rows 79.3, 64 rows
-// 79.1, 96 rows 79.0; 4096^2: 24 .. 48 rows within 1 % (64 rows: -4 %, too few tiles).  fp32 gains 2 % from 64 rows
-// (147.0 vs 143.9).  Smaller lattices take 16-row tiles so that enough tiles remain (profiles/r02_t2_rows_sweep.log,
-// r02_t2_small_sweep.log: 1536^2 45.4 (16 rows) vs 39.5 (32 rows) GLUPS).
+// fewer tiles to balance over 148 SMs x 2 CTAs.  Two regimes, both measured at 16384^2 fp64 EXACT (GLUPS):
+//   burst (fresh lattice, 50 steps, cool GPU = bench.py's timed region; tools/t2_burst_rows.py, profiles/r02_t2_rows_burst.log):
+//     32 rows 87.49, 36 rows 87.61, 40 rows 87.76, 48 rows 87.76, 64 rows 87.17, 74 rows 86.59, 96 rows 86.17
+//   sustained (interleaved A/B in one process under the power cap; tools/t2_env_ab.py, profiles/r02_t2_rows_ab.log):
+//     24 rows 80.2, 32 rows 80.1-81.8, 48 rows 83.0, 64 rows 82.0-83.5, 96 rows 83.0, 128 rows 82.6
+// 48 rows is the best of both (the saved arithmetic also saves power).  8192^2 sustained: 32 rows 78.8, 48 rows 79.3, 64
+// rows 79.1; 4096^2: 24 .. 48 rows within 1 %, 64 rows -4 % (too few tiles); 2048^2: 48 rows 50.7 vs 60.7 (32 rows) / 60.1
+// (16 rows).  fp32 gains 2 % from 64 rows (147.0 vs 143.9).  Smaller lattices take 16-row tiles so that enough tiles
+// remain (profiles/r02_t2_rows_sweep.log, r02_t2_small_sweep.log: 1536^2 45.4 (16 rows) vs 39.5 (32 rows) GLUPS).
 int t2_rows_for(const lb_lattice *L)
 {
     if (L->t2_rows > 0) return L->t2_rows;
     const long long tl = t2_tiles_over(L->cfg.lny);
     auto tiles = [&](int rows) { return tl * ((L->cfg.lnx - 4 + rows - 1) / rows); };
     if (L->cfg.dtype == LB_F32 && tiles(64) >= 1024) return 64;
-    if (tiles(96) >= 8192) return 96;
-    if (tiles(64) >= 4096) return 64;
+    if (tiles(48) >= 800) return 48;
     return tiles(32) >= 1024 ? 32 : 16;
 }
 
@@ -300,13 +302,13 @@ int launch_double_any(lb_lattice *L, int phases = 7, cudaStream_t fs = nullptr)
 // The second stream and the events of the overlapped pass (created outside any stream capture).
 int ensure_frame_stream(lb_lattice *L)
 {
-    if (L->s_frame) return 0;
+    if (L->s_frame) return 0;                // set last: a partial failure is retried (lb_destroy frees what exists)
     int least = 0, greatest = 0;
     LBM_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+    if (!L->ev_fork) LBM_CUDA(cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming));
+    if (!L->ev_int) LBM_CUDA(cudaEventCreateWithFlags(&L->ev_int, cudaEventDisableTiming));
+    if (!L->ev_frm) LBM_CUDA(cudaEventCreateWithFlags(&L->ev_frm, cudaEventDisableTiming));
     LBM_CUDA(cudaStreamCreateWithPriority(&L->s_frame, cudaStreamNonBlocking, greatest));   // frame CTAs slip in between the interior's
-    LBM_CUDA(cudaEventCreateWithFlags(&L->ev_fork, cudaEventDisableTiming));
-    LBM_CUDA(cudaEventCreateWithFlags(&L->ev_int, cudaEventDisableTiming));
-    LBM_CUDA(cudaEventCreateWithFlags(&L->ev_frm, cudaEventDisableTiming));
     return 0;
 }
 

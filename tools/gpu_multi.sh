@@ -6,5 +6,5 @@ nvidia-smi -L | head -8
 timeout 1200 python -m pytest tests/test_gpu_multi.py -v > gpurun_out/r02_pytest_multi_n$N.log 2>&1; tail -12 gpurun_out/r02_pytest_multi_n$N.log
 timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29517 bench.py --gpus $N --steps 20 --warmup 5 > gpurun_out/r02_bench_n$N.json 2> gpurun_out/r02_bench_n$N.err
 tail -c 5500 gpurun_out/r02_bench_n$N.json; tail -3 gpurun_out/r02_bench_n$N.err
-timeout 300 python tools/host_link_probe.py 2>&1 | tee gpurun_out/r02_host_links_n$N.json | tail -2
-lscpu | grep -E "Model name|Socket|NUMA node|^CPU\(s\)" > gpurun_out/r02_host_cpu.txt; free -g | head -2 >> gpurun_out/r02_host_cpu.txt; cat gpurun_out/r02_host_cpu.txt
+
+
