@@ -354,6 +354,7 @@ def main():
     b = lat.blockinfo
     t2 = args.temporal == 2 and lat.block.temporal_active
     steps_per_pass = 2 if t2 else 1
+    tile_rows = lat.block.temporal_rows if t2 else None
     passes = args.steps // steps_per_pass + (args.steps % steps_per_pass)
     per_step_ms = ms / args.steps
     per_pass_ms = ms / passes
@@ -506,7 +507,9 @@ def main():
                 "warmup": args.warmup, "ms_per_step": per_step_ms, "higher_is_better": True, "scaling": scaling,
                 "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": desc, "nx": nx, "ny": ny, "ndx": ndx, "ndy": ndy, "omega": omega, "u0": 0.1,
-                           "arith": args.arith, "steps_per_hbm_pass": steps_per_pass,
+                           "arith": args.arith, "steps_per_hbm_pass": steps_per_pass, "fused_tile_rows": tile_rows,
+                           "frame_kernels": ("concurrent with the fused interior kernel (second stream)"
+                                             if t2 and os.environ.get("LBM_T2_OVERLAP", "1") != "0" else None),
                            "single_step_roofline_mlups": peak * 1e9 / BYTES_PER_CELL / 1e6,
                            "halo": "in-kernel peer stores over NVLink (CUDA IPC), device-side flags",
                            "numa_bound_cpus": (len(numa) if numa else None),
