@@ -55,3 +55,24 @@ def test_product_arm_fails_loudly_without_gpu():
     r = run_bench(["--steps", "1", "--warmup", "3", "--no-e2e", "--no-cpu-baseline"])
     assert r.returncode != 0
     assert r.stdout.strip() == ""          # no fabricated line
+
+
+def test_roofline_traffic_is_reproducible_from_the_committed_ncu_logs(tmp_path):
+    """`roofline.traffic` in bench.py's line comes from profiles/r02_kernel_dram.json; that file must be exactly what
+    tools/ncu_dram_summary.py derives from the committed ncu launch lists of the bench command."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    committed = json.load(open(os.path.join(root, "profiles", "r02_kernel_dram.json")))
+    out = tmp_path / "dram.json"
+    subprocess.run([sys.executable, os.path.join(root, "tools", "ncu_dram_summary.py"), str(out),
+                    "exact+t2:268435456:profiles/r02_launches_weak16384.csv",
+                    "exact:268435456:profiles/r02_launches_weak16384_t1.csv"], cwd=root, check=True, stdout=subprocess.DEVNULL)
+    derived = json.load(open(out))
+    assert derived == committed
+    t2 = [c for c in committed["captures"] if c["arith"] == "exact+t2"][0]
+    assert 1.0 <= t2["dram_bytes_per_launch"] / t2["algorithmic_bytes_per_launch"] < 1.05      # redundant halo reads only
+    import bench
+    got = bench.ncu_traffic_per_launch("exact+t2", 268435456)
+    assert got and got["dram_bytes_per_launch"] == t2["dram_bytes_per_launch"]
