@@ -24,6 +24,9 @@ What each fixture pins (reference file:line):
   simple_sliding_lid.npz  slidingLid.py:33-108                             (bit-exact vs numpy oracle)
   table_sliding_lid_mpi.npz  slidingLidMPI.py:123-204,264-268 (full-range bounce, one rank)      (bit-exact)
   table_obstacle_channel.npz obstacle_canal.py:303-339,413-458 (methods of obstacleWindTunnel)   (bit-exact)
+  simpleflows_test_pins.npz  tests/simpleFlowsTest.py: the reference's OWN unit tests for this path, executed
+                             (test_array_allChannel_streaming :260-297, test_faster_principal_calc / test_equilibrium
+                             :676-720) and their helper functions (:928-990) evaluated on recorded inputs  (bit-exact)
 """
 import ast
 import os
@@ -296,8 +299,59 @@ def gen_table_flows():
     np.savez_compressed(os.path.join(OUT, "table_obstacle_channel.npz"), **out)
 
 
+def gen_reference_test_pins():
+    """The unit tests the reference itself holds for this path.  The test classes are lifted
+    like the functions above and their methods RUN here (they must pass under this numpy); then the helper functions
+    they exercise are evaluated on recorded inputs so that the oracle and the GPU can be held against them."""
+    import unittest
+    path = "tests/simpleFlowsTest.py"
+    with open(os.path.join(REF, path)) as fh:
+        tree = ast.parse(fh.read())
+    helpers = ("stream", "equlibrium_function", "equilibrium_on_array_test", "calculate_3pincipal_values", "caluculate_real_values")
+    classes = ("testsInStreaming", "testsForNewCollision")
+    body = [n for n in tree.body
+            if (isinstance(n, ast.FunctionDef) and n.name in helpers) or (isinstance(n, ast.ClassDef) and n.name in classes)
+            or (isinstance(n, ast.Assign) and any(isinstance(t, ast.Name) and t.id == "c_ic" for t in n.targets))]
+    ns = {"np": np, "unittest": unittest}
+    exec(compile(ast.Module(body=body, type_ignores=[]), path, "exec"), ns)
+    ran = {}
+    for cls, method in (("testsInStreaming", "test_array_allChannel_streaming"), ("testsForNewCollision", "test_faster_principal_calc"),
+                        ("testsForNewCollision", "test_equilibrium")):
+        res = unittest.TestResult()
+        ns[cls](method).run(res)
+        assert res.testsRun == 1 and res.wasSuccessful(), (cls, method, res.errors, res.failures)
+        ran[method] = True
+    out = {"reference_tests_passed": np.array(sorted(ran))}
+    # the streaming test's pattern (simpleFlowsTest.py:262-272): a line of ones in every channel, one periodic step
+    grid = np.zeros((9, 9, 9))
+    for watch in range(1, 9):
+        grid[watch, 1, 1:8] = 1
+    out["stream_in"] = grid.copy()
+    ns["stream"](grid)                               # simpleFlowsTest.py:928-930 (== PyLB/Streaming.py)
+    out["stream_out"] = grid.copy()
+    # equilibrium: scalar form (:933-948) and array form (:951-968) on the test's uniform field and on random fields
+    rng = np.random.default_rng(11)
+    for tag, (rho, ux, uy) in {"uniform": (np.full((5, 4), 9.0), np.zeros((5, 4)), np.zeros((5, 4))),
+                               "random": (1 + 0.05 * rng.standard_normal((16, 12)), 0.1 * rng.standard_normal((16, 12)),
+                                          0.1 * rng.standard_normal((16, 12)))}.items():
+        arr = ns["equilibrium_on_array_test"](rho, ux, uy)
+        sca = np.empty_like(arr)
+        for k in range(rho.shape[0]):
+            for l in range(rho.shape[1]):
+                sca[:, k, l] = ns["equlibrium_function"](rho[k, l], ux[k, l], uy[k, l])
+        out.update({"rho_" + tag: rho, "ux_" + tag: ux, "uy_" + tag: uy, "feq_array_" + tag: arr, "feq_scalar_" + tag: sca})
+    # moments (:1088-1092 and the per-node form :971-976) of a perturbed equilibrium
+    f = out["feq_array_random"] * (1 + 0.01 * rng.standard_normal((9, 16, 12)))
+    rho, ux, uy = ns["caluculate_real_values"](f)
+    out.update({"mom_f": f, "mom_rho": rho, "mom_ux": ux, "mom_uy": uy})
+    node = np.array([ns["calculate_3pincipal_values"](f[:, 3, 7])])
+    out["mom_node_3_7"] = node
+    np.savez_compressed(os.path.join(OUT, "simpleflows_test_pins.npz"), **out)
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    gen_reference_test_pins()
     gen_streaming()
     gen_cavity_opt2_bb()
     gen_collide_test_ref()

@@ -259,3 +259,39 @@ def test_symbolic_grid_rejects_what_a_table_cannot_hold():
         g[1, 1, :] = 0.0
     with pytest.raises(RuntimeError):
         SymbolicGrid(4, 4).table()
+
+
+def test_reference_unit_tests_pin_the_oracle(golden_dir):
+    """The reference's OWN unit tests for this path (tests/simpleFlowsTest.py) were executed by
+    tests/make_golden.py (all three pass); their helper functions, evaluated on recorded inputs, pin the oracle."""
+    g = load(golden_dir, "simpleflows_test_pins.npz")
+    assert set(g["reference_tests_passed"]) == {"test_array_allChannel_streaming", "test_faster_principal_calc", "test_equilibrium"}
+    # streaming convention, simpleFlowsTest.py:260-297: one line of ones per channel moves by its lattice velocity
+    src = g["stream_in"]
+    out = src.copy()
+    orc.stream(out)
+    assert np.array_equal(out, g["stream_out"])
+    pulled = np.empty_like(src)
+    orc.periodic_step_pull(src, pulled, 1.0, do_collide=False)          # the gather form the kernels use
+    assert np.array_equal(pulled, out)
+    moves = {1: (1, 0), 2: (0, 1), 3: (-1, 0), 4: (0, -1), 5: (1, 1), 6: (-1, 1), 7: (-1, -1), 8: (1, -1)}     # the test's eight assertion loops
+    for ch, (dx, dy) in moves.items():
+        for i in range(1, 8):
+            assert src[ch, i, 1] == out[ch, i + dx, 1 + dy]
+    # equilibrium, :700-720 (array form == scalar form, exactly, on the test's uniform field) and the helpers :933-968
+    for tag in ("uniform", "random"):
+        rho, ux, uy = g["rho_" + tag], g["ux_" + tag], g["uy_" + tag]
+        assert np.array_equal(sf.feq(rho, ux, uy), g["feq_array_" + tag])
+        if tag == "uniform":
+            assert np.array_equal(g["feq_array_" + tag], g["feq_scalar_" + tag])          # what the reference test asserts
+        else:
+            # For u != 0 the reference's scalar helper (:933-948) writes channels 6 and 8 with +-3(ux + uy) where the array
+            # form (:951-968, the one the simulators use: PoiseuilleFlow.py:25-42) has +-3(ux - uy); the reference only
+            # asserts their equality on a field at rest.  The other seven channels agree to rounding.
+            same = [0, 1, 2, 3, 4, 5, 7]
+            assert rel_err(g["feq_scalar_" + tag][same], g["feq_array_" + tag][same]) < 1e-14
+    # moments, :676-698 and the helpers :971-976, :1088-1092
+    rho, ux, uy = sf.moments(g["mom_f"])
+    assert np.array_equal(rho, g["mom_rho"]) and np.array_equal(ux, g["mom_ux"]) and np.array_equal(uy, g["mom_uy"])
+    node = g["mom_node_3_7"][0]
+    assert abs(node[0] - rho[3, 7]) <= 2e-16 * abs(rho[3, 7]) and abs(node[1] - ux[3, 7]) < 1e-16 and abs(node[2] - uy[3, 7]) < 1e-16
